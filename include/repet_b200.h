@@ -1,0 +1,127 @@
+/*
+ * repet_b200.h -- C ABI of the B200-native REPET separation path (librepet_b200.so).
+ *
+ * The reference (zafarrafii/REPET-Python, repet.py) has no FFI: its boundary is the Python
+ * module surface `repet.original/extended/adaptive/sim/simonline(audio_signal, fs)` plus the
+ * private helpers `_stft ... _simmask`.  Each entry point below names the reference
+ * function (repet.py line) it replaces; `repet-python_b200/repet/_host.py` is the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no torch / numpy types.  Every function returns an int
+ *    status: 0 = REPET_OK, negative = error; `repet_last_error(h)` gives the message.
+ *  - "_dev" functions take DEVICE pointers and enqueue on the handle's stream without
+ *    synchronising (unless a host output such as `periods_host` is requested).  The others
+ *    take HOST pointers and include the host<->device copies.
+ *  - Audio is fp32 planar [clip][channel][sample] unless the name says f64 (the reference's
+ *    float64 (sample, channel) NumPy layout, repet.py:73-77).
+ *  - The caller owns every buffer.  Calls on one handle are stream-ordered and not
+ *    re-entrant; use one handle per GPU and per host thread.
+ *  - All derived integers (period range in frames, cutoff bin, segment sizes ...) are computed
+ *    by the host with the reference's own Python expressions and passed in `repet_params`.
+ */
+#ifndef REPET_B200_H
+#define REPET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REPET_OK 0
+#define REPET_E_INVALID_ARG (-1) /* maps to ValueError on the Python side (quirk Q17) */
+#define REPET_E_TOO_SHORT (-2)   /* clip too short for the period search: ValueError in the reference */
+#define REPET_E_CUDA (-3)
+#define REPET_E_OOM (-4)
+#define REPET_E_UNSUPPORTED (-5) /* e.g. a window length this build has no transform for */
+
+typedef struct repet_handle repet_handle;
+
+/* Derived parameters; host computes them exactly as the reference does. */
+typedef struct repet_params {
+    int32_t window_length;    /* N  = 2^ceil(log2(0.04 fs))              repet.py:130 */
+    int32_t step_length;      /* H  = N/2                                repet.py:132 */
+    int32_t period_lo;        /* round(period_range[0]*fs/H)             repet.py:165 */
+    int32_t period_hi;        /* round(period_range[1]*fs/H)             repet.py:165 */
+    int32_t cutoff_bins;      /* round(cutoff_frequency*N/fs)            repet.py:173 */
+    int32_t segment_length;   /* extended: samples (repet.py:266); adaptive: frames (repet.py:519) */
+    int32_t segment_step;     /* extended: samples (repet.py:267); adaptive: frames (repet.py:520) */
+    int32_t filter_order;     /* adaptive median order                   repet.py:54   */
+    int32_t similarity_distance; /* frames                               repet.py:670 */
+    int32_t similarity_number;   /*                                      repet.py:60  */
+    int32_t buffer_frames;    /* simonline ring length in frames         repet.py:787 */
+    int32_t reserved0;
+    double similarity_threshold; /*                                      repet.py:58  */
+    double cola_gain;         /* sum(window[0:N:H])                      repet.py:1103 */
+} repet_params;
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+int repet_create(int device, repet_handle** out);
+int repet_destroy(repet_handle* h);
+const char* repet_last_error(repet_handle* h);
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL restores the handle's own. */
+int repet_set_stream(repet_handle* h, void* cuda_stream);
+/* Analysis window, HOST pointer, n = window length (built with SciPy's periodic Hamming by the
+ * host, repet.py:131 -- SciPy's values differ from the closed form by up to 1 ulp). */
+int repet_set_window(repet_handle* h, const double* window, int n);
+/* Cap on the workspace (bytes) a batch call may use per chunk of clips; 0 = default. */
+int repet_set_workspace_limit(repet_handle* h, uint64_t bytes);
+int repet_synchronize(repet_handle* h);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+uint64_t repet_launch_count(repet_handle* h);
+const char* repet_version(void);
+
+/* Per-kernel device time for the roofline report: with profiling on, every launch is
+ * bracketed by a CUDA event pair on the handle's stream.  repet_profile_read synchronises the
+ * stream and returns accumulated milliseconds and launch counts per kernel id. */
+#define REPET_NUM_KERNELS 8
+#define REPET_K_STFT 0
+#define REPET_K_BEAT 1
+#define REPET_K_PERIODS 2
+#define REPET_K_MODEL 3
+#define REPET_K_MASK_ISTFT 4
+#define REPET_K_CONVERT 5
+int repet_set_profiling(repet_handle* h, int on);
+int repet_profile_read(repet_handle* h, double* ms, uint64_t* counts, int reset);
+const char* repet_kernel_name(int id);
+
+/* ---- drivers ---------------------------------------------------------------------------- */
+/* repet.original (repet.py:67-202) over a batch of equally long clips, device resident.
+ * audio/background: [n_clips][n_channels][n_samples] fp32 on the device.
+ * periods_dev: optional int32[n_clips] on the device; periods_host: optional host copy
+ * (forces a stream synchronise). */
+int repet_original_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host);
+/* Same with HOST buffers (pinned memory recommended); copies are chunked and overlapped. */
+int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                         const repet_params* p, float* background, int32_t* periods_host);
+/* The reference's exact calling convention for one clip: float64 (n_samples, n_channels)
+ * in and out, host pointers (repet.py:73-77). */
+int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels,
+                       const repet_params* p, double* background, int32_t* period_host);
+
+/* ---- helpers (unit parity with the reference's private functions), HOST pointers -------- */
+/* _stft (repet.py:1001-1060) of n_channels (1 or 2) real signals at once.
+ * signal: [n_channels][n_samples] fp32; spectrum: [n_frames][n_channels][N/2] float2 with
+ * bin 0 = (DC.re, Nyquist.re); power (optional): [n_frames][1025] fp32 = (mean_c |X|)^2. */
+int repet_stft(repet_handle* h, const float* signal, int n_channels, int64_t n_samples, float* spectrum,
+               float* power, int32_t* n_frames_out);
+/* _istft (repet.py:1063-1105): spectrum as above -> signal [n_channels][(n_frames-1)*H]. */
+int repet_istft(repet_handle* h, const float* spectrum, int n_channels, int n_frames, double cola_gain,
+                float* signal);
+/* _beatspectrum (repet.py:1142-1158): spectrogram [n_frames][n_rows] fp32 (time major),
+ * n_rows <= 1025, 2*n_frames-1 <= 2048 -> beat[n_frames] float64. */
+int repet_beatspectrum(repet_handle* h, const float* spectrogram, int n_frames, int n_rows, double* beat);
+/* _periods on the device beat spectrum of the same input (repet.py:1249-1291): returns the
+ * period for lags [period_lo, min(period_hi, n_frames/3)). */
+int repet_period(repet_handle* h, const float* spectrogram, int n_frames, int n_rows, int period_lo, int period_hi,
+                 int32_t* period);
+/* _mask (repet.py:1386-1458): magnitude spectrogram [n_frames][1025] fp32 + period ->
+ * mask [n_frames][1025] fp32. */
+int repet_mask(repet_handle* h, const float* magnitude, int n_frames, int period, float* mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPET_B200_H */

@@ -1,0 +1,71 @@
+// Launch-side declarations shared by repet_kernels.cu (device code) and repet_abi.cu (C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace repet {
+
+constexpr int WIN_N = 2048;        // STFT window length supported by this build (fs in (25.6 kHz, 51.2 kHz])
+constexpr int HOP = WIN_N / 2;     // step length H
+constexpr int NBIN = WIN_N / 2 + 1;  // F = 1025 magnitude bins
+constexpr int XPITCH = WIN_N / 2;  // float2 per (frame, channel): bin 0 holds (DC.re, Nyquist.re)
+constexpr int PPITCH = 1032;       // floats per frame row of P / model (1025 rounded up to 32 B)
+constexpr int BEAT_L = 2048;       // FFT length of the beat-spectrum transforms
+constexpr int MAX_MEDIAN_REGS = 32;  // sorting-network path handles up to 32 gathered values
+
+// A batch of equally long items cut out of planar audio [clip][channel][sample]:
+// item = clip * seg_per_clip + seg starts at clip*clip_stride + seg*seg_stride (+ c*chan_stride).
+// `original` uses seg_per_clip = 1; `extended` lays its 10 s segments out this way.
+struct Geom {
+    int n_items;
+    int seg_per_clip;
+    long long clip_stride;
+    long long seg_stride;
+    long long chan_stride;
+    long long first_offset;  // added to every item start
+    int S;                   // samples per item
+    int T;                   // STFT frames per item
+};
+
+struct FftTables {
+    const float2* tw1;  // [15][128]  W_2048^(m*k1)
+    const float2* tw2;  // [16][8]    W_128^(m2*k2)
+};
+
+enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2 };
+
+// k_stft: audio -> X (half spectra, both channels) [+ P = (mean_c |X|)^2 or mean_c |X|]
+void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,
+                 float* P, int pmode, int frames_per_cta);
+
+// k_beat: P rows [t_first, t_first + t_len) of every item (zero outside [0, T)) -> partial PSD sums
+// psd_part[item][part][2048]
+void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
+                 FftTables tb, float* psd_part, int n_parts, int f_per_part);
+
+// k_periods: partial PSDs -> beat spectrum b[l] (optional) and argmax period per beat item (fp64)
+void launch_periods(cudaStream_t st, const float* psd_part, int n_beat_items, int n_parts, int t_len, double norm_rows,
+                    int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out, int beat_pitch, int* period,
+                    double* stats);
+
+// k_model: median over the period-strided frames of every phase -> model[item][c][q][PPITCH]
+void launch_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
+                  float* model);
+
+// k_mask_istft: soft mask from the periodic model, high-pass, Hermitian pack, inverse FFT, overlap-add
+void launch_mask_istft(cudaStream_t st, const float2* X, Geom g_out, int nch, const int* period, int pmax,
+                       const float* model, int cutoff, float scale, FftTables tb, float* out, int blocks_per_cta);
+
+// plain ISTFT of caller-provided half spectra (helper-level entry point)
+void launch_istft(cudaStream_t st, const float2* X, Geom g_out, int nch, float scale, FftTables tb, float* out,
+                  int blocks_per_cta);
+
+// mask only (helper-level): writes M[item][c][T][PPITCH]
+void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
+                      const float* model, float* mask_out);
+
+// layout converters for the float64 (S, C) NumPy convention of the reference API
+void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out);
+void launch_planar_to_f64_interleaved(cudaStream_t st, const float* in, long long S, int C, double* out);
+
+}  // namespace repet

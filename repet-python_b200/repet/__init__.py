@@ -1,0 +1,219 @@
+"""
+repet -- drop-in, B200-native replacement for zafarrafii/REPET-Python's `repet.py`.
+
+Same module surface as the reference (repet.py:15-25, 42-63): the five separation
+functions take and return NumPy arrays, the nine tunables are module globals read at call
+time, `wavread` / `wavwrite` / `specshow` keep their signatures.  The arithmetic runs in
+hand-written sm_100a CUDA kernels behind the C ABI of `include/repet_b200.h`
+(librepet_b200.so, loaded by `_host.py` through ctypes).  There is no CPU fallback: without
+the library or without a CUDA device every separation call raises.
+
+Functions:
+    original - Compute the original REPET.
+    extended - Compute REPET extended.
+    adaptive - Compute the adaptive REPET.
+    sim - Compute REPET-SIM.
+    simonline - Compute the online REPET-SIM.
+
+Other:
+    wavread - Read a WAVE file (using SciPy).
+    wavwrite - Write a WAVE file (using SciPy).
+    specshow - Display an spectrogram in dB, seconds, and Hz.
+
+Beyond the reference: `original_batch` for many clips per call.
+"""
+
+import numpy as np
+
+from . import _host
+
+# Public variables (repet.py:42-63) -- read at call time, so `repet.period_range = [1, 5]` works
+# Cutoff frequency in Hz for the dual high-pass filter of the foreground
+cutoff_frequency = 100
+
+# Period range in seconds for the beat spectrum (original, extended, adaptive)
+period_range = [1, 10]
+
+# Segment length and step in seconds (extended, adaptive)
+segment_length = 10
+segment_step = 5
+
+# Filter order for the median filter (adaptive)
+filter_order = 5
+
+# Minimal threshold for two similar frames in [0,1], minimal distance between two similar frames in
+# seconds, and maximal number of similar frames for every frame (sim, simonline)
+similarity_threshold = 0
+similarity_distance = 1
+similarity_number = 100
+
+# Buffer length in seconds (simonline)
+buffer_length = 10
+
+_TUNABLES = (
+    "cutoff_frequency",
+    "period_range",
+    "segment_length",
+    "segment_step",
+    "filter_order",
+    "similarity_threshold",
+    "similarity_distance",
+    "similarity_number",
+    "buffer_length",
+)
+
+
+def _tunables():
+    module = globals()
+    return {name: module[name] for name in _TUNABLES}
+
+
+# ----------------------------------------------------------------------------------------
+# Public functions
+# ----------------------------------------------------------------------------------------
+def original(audio_signal, sampling_frequency):
+    """
+    Compute the original REPET (repet.py:67-202).
+
+    Inputs:
+        audio_signal: audio signal (number_samples, number_channels)
+        sampling_frequency: sampling frequency in Hz
+    Output:
+        background_signal: background signal (number_samples, number_channels)
+    """
+    return _host.original_f64(audio_signal, sampling_frequency, _tunables())
+
+
+def original_batch(audio_signals, sampling_frequency):
+    """
+    The original REPET over a batch of equally long clips in one call.
+
+    Inputs:
+        audio_signals: float32 array (number_clips, number_channels, number_samples), planar
+        sampling_frequency: sampling frequency in Hz
+    Outputs:
+        background_signals: float32 array of the same shape
+        repeating_periods: int32 array (number_clips,), in time frames
+    """
+    return _host.original_batch(audio_signals, sampling_frequency, _tunables())
+
+
+def extended(audio_signal, sampling_frequency):
+    """Compute REPET extended (repet.py:205-419)."""
+    return _host.extended_f64(audio_signal, sampling_frequency, _tunables())
+
+
+def adaptive(audio_signal, sampling_frequency):
+    """Compute the adaptive REPET (repet.py:422-568)."""
+    return _host.adaptive_f64(audio_signal, sampling_frequency, _tunables())
+
+
+def sim(audio_signal, sampling_frequency):
+    """Compute REPET-SIM (repet.py:571-709)."""
+    return _host.sim_f64(audio_signal, sampling_frequency, _tunables())
+
+
+def simonline(audio_signal, sampling_frequency):
+    """Compute the online REPET-SIM (repet.py:712-911)."""
+    return _host.simonline_f64(audio_signal, sampling_frequency, _tunables())
+
+
+def wavread(audio_file):
+    """
+    Read a WAVE file (using SciPy) (repet.py:914-931).
+
+    Input:
+        audio_file: path to an audio file
+    Outputs:
+        audio_signal: audio signal (number_samples, number_channels)
+        sampling_frequency: sampling frequency in Hz
+    """
+    import scipy.io.wavfile
+
+    sampling_frequency, audio_signal = scipy.io.wavfile.read(audio_file)
+    audio_signal = audio_signal / pow(2, audio_signal.itemsize * 8 - 1)
+    return audio_signal, sampling_frequency
+
+
+def wavwrite(audio_signal, sampling_frequency, audio_file):
+    """Write a WAVE file (using SciPy) (repet.py:934-946)."""
+    import scipy.io.wavfile
+
+    scipy.io.wavfile.write(audio_file, sampling_frequency, audio_signal)
+
+
+def specshow(audio_spectrogram, time_duration, maximum_frequency, xtick_step=1, ytick_step=1000):
+    """
+    Display a spectrogram in dB, seconds, and Hz (repet.py:949-997).  matplotlib is imported
+    lazily: it is a plotting convenience, not part of the separation path.
+    """
+    import matplotlib.pyplot as plt
+
+    number_frequencies, number_times = np.shape(audio_spectrogram)
+    time_resolution = number_times / time_duration
+    frequency_resolution = number_frequencies / maximum_frequency
+    xtick_locations = np.arange(xtick_step * time_resolution, number_times, xtick_step * time_resolution)
+    xtick_labels = np.arange(xtick_step, time_duration, xtick_step).astype(int)
+    ytick_locations = np.arange(ytick_step * frequency_resolution, number_frequencies, ytick_step * frequency_resolution)
+    ytick_labels = np.arange(ytick_step, maximum_frequency, ytick_step).astype(int)
+    plt.imshow(20 * np.log10(audio_spectrogram), aspect="auto", cmap="jet", origin="lower")
+    plt.xticks(ticks=xtick_locations, labels=xtick_labels)
+    plt.yticks(ticks=ytick_locations, labels=ytick_labels)
+    plt.xlabel("Time (s)")
+    plt.ylabel("Frequency (Hz)")
+
+
+# ----------------------------------------------------------------------------------------
+# Private functions with the reference's shapes (repet.py:1001-1545)
+# ----------------------------------------------------------------------------------------
+def _stft(audio_signal, window_function, step_length):
+    """
+    Short-time Fourier transform (repet.py:1001-1060).
+
+    Inputs:
+        audio_signal: audio signal (number_samples,)
+        window_function: window function (window_length,)
+        step_length: step length in samples
+    Output:
+        audio_stft: audio STFT (window_length, number_times), full mirrored spectrum
+    """
+    audio_signal = np.asarray(audio_signal)
+    half = _host.stft_half(audio_signal[np.newaxis, :], window_function, step_length)[0]  # (T, F)
+    window_length = len(window_function)
+    audio_stft = np.empty((window_length, half.shape[0]), dtype=complex)
+    audio_stft[0 : window_length // 2 + 1, :] = half.T
+    audio_stft[window_length // 2 + 1 :, :] = np.conj(half[:, window_length // 2 - 1 : 0 : -1].T)
+    return audio_stft
+
+
+def _istft(audio_stft, window_function, step_length):
+    """
+    Inverse short-time Fourier transform (repet.py:1063-1105): real(ifft) of every frame,
+    overlap-add, trim, divide by the COLA gain.
+
+    Inputs:
+        audio_stft: audio STFT (window_length, number_times)
+        window_function: window function (window_length,)
+        step_length: step length in samples
+    Output:
+        audio_signal: audio signal (number_samples,)
+    """
+    audio_stft = np.asarray(audio_stft, dtype=complex)
+    window_length = audio_stft.shape[0]
+    half = window_length // 2
+    # real(ifft(Y)) only sees the Hermitian part of Y: Yh[k] = (Y[k] + conj(Y[N-k]))/2
+    mirror = np.conj(audio_stft[(-np.arange(window_length)) % window_length, :])
+    hermitian = 0.5 * (audio_stft + mirror)
+    signal = _host.istft_half(hermitian[np.newaxis, 0 : half + 1, :].transpose(0, 2, 1), window_function, step_length)
+    return signal[0].astype(float)
+
+
+def _beatspectrum(audio_spectrogram):
+    """Beat spectrum (repet.py:1142-1158): (number_frequencies, number_times) -> (number_times,)."""
+    return _host.beatspectrum(audio_spectrogram)
+
+
+def _mask(audio_spectrogram, repeating_period):
+    """Repeating mask for REPET (repet.py:1386-1458): (number_frequencies, number_times), period ->
+    (number_frequencies, number_times)."""
+    return _host.mask(audio_spectrogram, repeating_period)

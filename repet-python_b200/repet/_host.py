@@ -1,0 +1,390 @@
+"""
+ctypes binding of librepet_b200.so (include/repet_b200.h) and the host-side parameter
+derivation of the REPET drivers.
+
+This is the reference-side binding of INTEGRATION.md: every derived integer is computed with
+the reference's own Python expression (cited per line), the samples go to the library
+untouched, and there is NO CPU fallback -- if the CUDA library or a CUDA device is missing
+the calls raise.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "librepet_b200.so")
+
+REPET_OK = 0
+REPET_E_INVALID_ARG = -1
+REPET_E_TOO_SHORT = -2
+REPET_E_CUDA = -3
+REPET_E_OOM = -4
+REPET_E_UNSUPPORTED = -5
+
+
+class RepetParams(ctypes.Structure):
+    """struct repet_params of include/repet_b200.h."""
+
+    _fields_ = [
+        ("window_length", ctypes.c_int32),
+        ("step_length", ctypes.c_int32),
+        ("period_lo", ctypes.c_int32),
+        ("period_hi", ctypes.c_int32),
+        ("cutoff_bins", ctypes.c_int32),
+        ("segment_length", ctypes.c_int32),
+        ("segment_step", ctypes.c_int32),
+        ("filter_order", ctypes.c_int32),
+        ("similarity_distance", ctypes.c_int32),
+        ("similarity_number", ctypes.c_int32),
+        ("buffer_frames", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
+        ("similarity_threshold", ctypes.c_double),
+        ("cola_gain", ctypes.c_double),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_c_int = ctypes.c_int
+_c_i64 = ctypes.c_int64
+_c_u64 = ctypes.c_uint64
+_vp = ctypes.c_void_p
+_pp = ctypes.POINTER(RepetParams)
+
+# name -> (restype, argtypes); must list every symbol include/repet_b200.h declares
+SIGNATURES = {
+    "repet_version": (ctypes.c_char_p, []),
+    "repet_create": (_c_int, [_c_int, ctypes.POINTER(_vp)]),
+    "repet_destroy": (_c_int, [_vp]),
+    "repet_last_error": (ctypes.c_char_p, [_vp]),
+    "repet_set_stream": (_c_int, [_vp, _vp]),
+    "repet_set_window": (_c_int, [_vp, _vp, _c_int]),
+    "repet_set_workspace_limit": (_c_int, [_vp, _c_u64]),
+    "repet_synchronize": (_c_int, [_vp]),
+    "repet_launch_count": (_c_u64, [_vp]),
+    "repet_set_profiling": (_c_int, [_vp, _c_int]),
+    "repet_profile_read": (_c_int, [_vp, _vp, _vp, _c_int]),
+    "repet_kernel_name": (ctypes.c_char_p, [_c_int]),
+    "repet_original_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
+    "repet_original_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_original_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp]),
+    "repet_stft": (_c_int, [_vp, _vp, _c_int, _c_i64, _vp, _vp, _vp]),
+    "repet_istft": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_double, _vp]),
+    "repet_beatspectrum": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
+    "repet_period": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "repet_mask": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
+}
+
+
+def load_library():
+    """Load librepet_b200.so; raises if it has not been built (python repet-python_b200/build.py)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "librepet_b200.so is missing at %s -- build it with `python repet-python_b200/build.py`; "
+                "there is no CPU fallback" % LIB_PATH
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+class RepetError(RuntimeError):
+    pass
+
+
+def _ptr(array):
+    return array.ctypes.data_as(_vp) if array is not None else None
+
+
+class Handle:
+    """One library handle (one GPU, one host thread)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        handle = _vp()
+        rc = self.lib.repet_create(int(device), ctypes.byref(handle))
+        if rc != REPET_OK:
+            raise RepetError(
+                "repet_create(device=%d) failed with status %d: no usable CUDA device (there is no CPU fallback)"
+                % (device, rc)
+            )
+        self.h = handle
+        self.device = int(device)
+        self._window_key = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.repet_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc == REPET_OK:
+            return
+        message = self.lib.repet_last_error(self.h).decode("utf-8", "replace")
+        if rc in (REPET_E_INVALID_ARG, REPET_E_TOO_SHORT):
+            raise ValueError(message)  # what NumPy raises inside the reference (quirk Q17)
+        if rc == REPET_E_UNSUPPORTED:
+            raise NotImplementedError(message)
+        if rc == REPET_E_OOM:
+            raise MemoryError(message)
+        raise RepetError("status %d: %s" % (rc, message))
+
+    def set_window(self, window_function, key=None):
+        window = np.ascontiguousarray(window_function, dtype=np.float64)
+        self.check(self.lib.repet_set_window(self.h, _ptr(window), len(window)))
+        self._window_key = key
+
+    def ensure_window(self, window_length):
+        """Upload the drivers' periodic Hamming window unless it is already the current one."""
+        if self._window_key != ("hamming", window_length):
+            self.set_window(hamming_window(window_length), key=("hamming", window_length))
+
+    def set_stream(self, cuda_stream_pointer):
+        self.check(self.lib.repet_set_stream(self.h, _vp(cuda_stream_pointer) if cuda_stream_pointer else None))
+
+    def set_workspace_limit(self, number_bytes):
+        self.check(self.lib.repet_set_workspace_limit(self.h, int(number_bytes)))
+
+    def synchronize(self):
+        self.check(self.lib.repet_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.repet_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self.check(self.lib.repet_set_profiling(self.h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        """{kernel name: (total ms, launches)} accumulated while profiling was on."""
+        ms = np.zeros(8, dtype=np.float64)
+        counts = np.zeros(8, dtype=np.uint64)
+        self.check(self.lib.repet_profile_read(self.h, _ptr(ms), _ptr(counts), 1 if reset else 0))
+        return {
+            self.lib.repet_kernel_name(i).decode(): (float(ms[i]), int(counts[i])) for i in range(8) if counts[i]
+        }
+
+
+_handles = {}
+
+
+def get_handle(device=None):
+    """Process-wide handle of a device (default: REPET_DEVICE or LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("REPET_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _handles:
+        _handles[device] = Handle(device)
+    return _handles[device]
+
+
+# ------------------------------------------------------------------------------------------
+# parameter derivation, with the reference's own expressions
+# ------------------------------------------------------------------------------------------
+def hamming_window(window_length):
+    """scipy.signal.hamming(N, sym=False) (repet.py:131); SciPy's own values, which differ
+    from the closed form by up to 1 ulp."""
+    import scipy.signal.windows
+
+    return scipy.signal.windows.hamming(window_length, sym=False)
+
+
+def derive_params(sampling_frequency, tunables):
+    """All derived integers of the five drivers."""
+    window_length = pow(2, int(np.ceil(np.log2(0.04 * sampling_frequency))))  # repet.py:130
+    step_length = int(window_length / 2)  # repet.py:132
+    window_function = hamming_window(window_length)
+    period_range2 = np.round(np.array(tunables["period_range"]) * sampling_frequency / step_length).astype(int)  # :165
+    cutoff_frequency2 = round(tunables["cutoff_frequency"] * window_length / sampling_frequency)  # :173
+    p = RepetParams()
+    p.window_length = window_length
+    p.step_length = step_length
+    p.period_lo = int(period_range2[0])
+    p.period_hi = int(period_range2[1])
+    p.cutoff_bins = int(cutoff_frequency2)
+    p.filter_order = int(tunables["filter_order"])
+    p.similarity_distance = int(round(tunables["similarity_distance"] * sampling_frequency / step_length))  # :670
+    p.similarity_number = int(tunables["similarity_number"])
+    p.similarity_threshold = float(tunables["similarity_threshold"])
+    p.buffer_frames = int(round((tunables["buffer_length"] * sampling_frequency) / step_length))  # :787
+    p.cola_gain = float(sum(window_function[0:window_length:step_length]))  # repet.py:1103
+    return p, window_function
+
+
+def number_of_frames(number_samples, window_length, step_length):
+    """repet.py:135-146."""
+    return int(np.ceil(((number_samples + 2 * int(np.floor(window_length / 2))) - window_length) / step_length)) + 1
+
+
+# ------------------------------------------------------------------------------------------
+# drivers
+# ------------------------------------------------------------------------------------------
+def original_f64(audio_signal, sampling_frequency, tunables, handle=None, return_period=False):
+    """repet.original with the reference's calling convention (repet.py:67-202)."""
+    number_samples, number_channels = np.shape(audio_signal)  # repet.py:125 (ValueError if not 2-D)
+    handle = handle or get_handle()
+    params, window_function = derive_params(sampling_frequency, tunables)
+    handle.ensure_window(params.window_length)
+    audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
+    background = np.empty((number_samples, number_channels), dtype=np.float64)
+    period = np.zeros(1, dtype=np.int32)
+    handle.check(
+        handle.lib.repet_original_f64(
+            handle.h, _ptr(audio), number_samples, number_channels, ctypes.byref(params), _ptr(background), _ptr(period)
+        )
+    )
+    if return_period:
+        return background, int(period[0])
+    return background
+
+
+def original_batch(audio, sampling_frequency, tunables, handle=None, out=None):
+    """`original` over a batch of clips: audio (B, C, S) float32 planar, host memory.
+    Returns (background (B, C, S) float32, periods (B,) int32)."""
+    handle = handle or get_handle()
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    if audio.ndim != 3:
+        raise ValueError("audio must have shape (clips, channels, samples)")
+    number_clips, number_channels, number_samples = audio.shape
+    params, _ = derive_params(sampling_frequency, tunables)
+    handle.ensure_window(params.window_length)
+    background = out if out is not None else np.empty_like(audio)
+    periods = np.zeros(number_clips, dtype=np.int32)
+    handle.check(
+        handle.lib.repet_original_batch(
+            handle.h, _ptr(audio), number_clips, number_channels, number_samples, ctypes.byref(params),
+            _ptr(background), _ptr(periods),
+        )
+    )
+    return background, periods
+
+
+def original_batch_device(audio_ptr, background_ptr, number_clips, number_channels, number_samples,
+                          sampling_frequency, tunables, handle=None, periods_ptr=None, periods_host=None):
+    """`original` over device-resident fp32 planar clips (raw device pointers, e.g.
+    torch.Tensor.data_ptr()).  Enqueues on the handle's stream; synchronises only when
+    `periods_host` (int32 array) is given."""
+    handle = handle or get_handle()
+    params, _ = derive_params(sampling_frequency, tunables)
+    handle.ensure_window(params.window_length)
+    handle.check(
+        handle.lib.repet_original_batch_dev(
+            handle.h, _vp(audio_ptr), number_clips, number_channels, number_samples, ctypes.byref(params),
+            _vp(background_ptr), _vp(periods_ptr) if periods_ptr else None, _ptr(periods_host),
+        )
+    )
+
+
+# ------------------------------------------------------------------------------------------
+# helpers with the reference's shapes
+# ------------------------------------------------------------------------------------------
+def stft_half(signals, window_function, step_length, handle=None, with_power=False):
+    """Half spectra of 1 or 2 real signals: signals (C, S) -> complex64 (C, T, F) [, power (T, F)]."""
+    handle = handle or get_handle()
+    window_length = len(window_function)
+    if step_length * 2 != window_length:
+        raise NotImplementedError("step_length must be window_length/2")
+    handle.set_window(window_function)
+    signals = np.ascontiguousarray(signals, dtype=np.float32)
+    number_channels, number_samples = signals.shape
+    number_times = number_of_frames(number_samples, window_length, step_length)
+    half = window_length // 2
+    packed = np.empty((number_times, number_channels, half, 2), dtype=np.float32)
+    power = np.empty((number_times, half + 1), dtype=np.float32) if with_power else None
+    frames = ctypes.c_int32(0)
+    handle.check(
+        handle.lib.repet_stft(
+            handle.h, _ptr(signals), number_channels, number_samples, _ptr(packed), _ptr(power), ctypes.byref(frames)
+        )
+    )
+    assert frames.value == number_times
+    spectrum = np.empty((number_channels, number_times, half + 1), dtype=np.complex64)
+    body = packed[..., 0] + 1j * packed[..., 1]
+    spectrum[:, :, :half] = np.transpose(body, (1, 0, 2))
+    spectrum[:, :, 0] = packed[:, :, 0, 0].T  # DC is real
+    spectrum[:, :, half] = packed[:, :, 0, 1].T  # Nyquist rides in bin 0's imaginary slot
+    if with_power:
+        return spectrum, power
+    return spectrum
+
+
+def istft_half(spectrum, window_function, step_length, handle=None):
+    """Inverse of stft_half: complex (C, T, F) -> float32 (C, (T-1)*H)."""
+    handle = handle or get_handle()
+    window_length = len(window_function)
+    half = window_length // 2
+    number_channels, number_times, number_frequencies = spectrum.shape
+    assert number_frequencies == half + 1
+    packed = np.empty((number_times, number_channels, half, 2), dtype=np.float32)
+    packed[..., 0] = np.transpose(spectrum[:, :, :half].real, (1, 0, 2))
+    packed[..., 1] = np.transpose(spectrum[:, :, :half].imag, (1, 0, 2))
+    packed[:, :, 0, 1] = spectrum[:, :, half].real.T
+    signal = np.empty((number_channels, (number_times - 1) * step_length), dtype=np.float32)
+    gain = float(sum(window_function[0:window_length:step_length]))
+    handle.check(handle.lib.repet_istft(handle.h, _ptr(packed), number_channels, number_times, gain, _ptr(signal)))
+    return signal
+
+
+def beatspectrum(audio_spectrogram, handle=None):
+    """_beatspectrum (repet.py:1142-1158): (F, T) magnitudes -> float64 (T,)."""
+    handle = handle or get_handle()
+    spectrogram = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)  # time major
+    number_times, number_rows = spectrogram.shape
+    beat = np.empty(number_times, dtype=np.float64)
+    handle.check(handle.lib.repet_beatspectrum(handle.h, _ptr(spectrogram), number_times, number_rows, _ptr(beat)))
+    return beat
+
+
+def period_of(audio_spectrogram, period_range2, handle=None):
+    """_periods(_beatspectrum(V), period_range2) (repet.py:1249-1291) for one spectrogram."""
+    handle = handle or get_handle()
+    spectrogram = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
+    number_times, number_rows = spectrogram.shape
+    period = np.zeros(1, dtype=np.int32)
+    handle.check(
+        handle.lib.repet_period(
+            handle.h, _ptr(spectrogram), number_times, number_rows, int(period_range2[0]), int(period_range2[1]), _ptr(period)
+        )
+    )
+    return int(period[0])
+
+
+def mask(audio_spectrogram, repeating_period, handle=None):
+    """_mask (repet.py:1386-1458): (1025, T) magnitudes, period -> float64 (1025, T)."""
+    handle = handle or get_handle()
+    magnitude = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
+    number_times, number_frequencies = magnitude.shape
+    if number_frequencies != 1025:
+        raise NotImplementedError("this build masks 1025-bin spectrograms (window_length 2048)")
+    out = np.empty((number_times, number_frequencies), dtype=np.float32)
+    handle.check(handle.lib.repet_mask(handle.h, _ptr(magnitude), number_times, int(repeating_period), _ptr(out)))
+    return out.T.astype(np.float64)
+
+
+def _not_built(name):
+    def raiser(*args, **kwargs):
+        raise NotImplementedError("repet.%s has no CUDA path in this build yet (there is no CPU fallback)" % name)
+
+    return raiser
+
+
+extended_f64 = _not_built("extended")
+adaptive_f64 = _not_built("adaptive")
+sim_f64 = _not_built("sim")
+simonline_f64 = _not_built("simonline")

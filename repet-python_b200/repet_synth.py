@@ -88,20 +88,35 @@ def make_clip(
     return out.astype(dtype)
 
 
+def _clip_job(args):
+    index, number_samples, number_channels, sampling_frequency, kwargs = args
+    return make_clip(index, number_samples, number_channels, sampling_frequency, **kwargs)
+
+
 def make_batch(first_index, number_clips, number_samples, number_channels=2, sampling_frequency=44100,
-               out=None, workers=None, **kwargs):
-    """Clips first_index .. first_index+number_clips-1 as (B, C, S) float32, generated on a
-    thread pool (NumPy releases the GIL in the heavy parts)."""
-    from concurrent.futures import ThreadPoolExecutor
+               out=None, workers=None, processes=False, **kwargs):
+    """Clips first_index .. first_index+number_clips-1 as (B, C, S) float32.
+
+    `processes=True` uses a fork pool (call it BEFORE CUDA is initialised in the process);
+    the default is a thread pool."""
     import os
 
     if out is None:
         out = np.empty((number_clips, number_channels, number_samples), dtype=np.float32)
-    workers = workers or min(32, os.cpu_count() or 1)
+    workers = max(1, workers or min(64, os.cpu_count() or 1))
+    jobs = [(first_index + i, number_samples, number_channels, sampling_frequency, kwargs) for i in range(number_clips)]
+    if processes and workers > 1 and number_clips > 1:
+        import multiprocessing
 
-    def fill(i):
-        out[i] = make_clip(first_index + i, number_samples, number_channels, sampling_frequency, **kwargs)
+        with multiprocessing.get_context("fork").Pool(min(workers, number_clips)) as pool:
+            for i, clip in enumerate(pool.imap(_clip_job, jobs, chunksize=1)):
+                out[i] = clip
+    else:
+        from concurrent.futures import ThreadPoolExecutor
 
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        list(pool.map(fill, range(number_clips)))
+        def fill(i):
+            out[i] = _clip_job(jobs[i])
+
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            list(pool.map(fill, range(number_clips)))
     return out
