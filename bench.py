@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workspace-mb", type=int, default=0, help="per-chunk workspace cap of the library (0 = default)")
+    ap.add_argument("--tune", default="", help="comma separated knob=value pairs for repet_set_tuning (experiments)")
     return ap.parse_args()
 
 
@@ -172,57 +173,68 @@ def config_dict(args, sample_clips=None):
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~5 ms DURING the timed region."""
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.running = False
+        self.thread = None
+        self.max_mhz = None
+        self.error = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # pragma: no cover
+            self.error = "nvml unavailable: %r" % (exc,)
+            return
+        self.running = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        n = self.nvml
+        flags = {
+            "hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+            "hw_thermal_slowdown": 0x40,
+            "sw_thermal_slowdown": 0x20,
+            "sw_power_cap": 0x4,
+        }
+        while self.running:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM)))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except AttributeError:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for name, bit in flags.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as exc:  # pragma: no cover
+                self.error = repr(exc)
+                break
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[5:9]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
-            "samples": len(sm),
-            "reasons": sorted(reasons),
+        self.running = False
+        if self.thread:
+            self.thread.join(timeout=2)
+        out = {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "samples": len(self.samples),
+            "reasons": sorted(self.reasons),
         }
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -272,9 +284,12 @@ def run_b200_arm(args, rank, local_rank, world):
             dist.barrier()
 
     handle = repet._host.Handle(local_rank)
+    if args.tune:
+        repet._host.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(","))})
     if args.workspace_mb:
         handle.set_workspace_limit(args.workspace_mb << 20)
-    stream = torch.cuda.current_stream(device)
+    stream = torch.cuda.Stream(device)  # everything below is enqueued on this one stream
+    torch.cuda.set_stream(stream)
     handle.set_stream(stream.cuda_stream)
 
     pinned_in = torch.from_numpy(host_audio).pin_memory()

@@ -60,7 +60,8 @@ typedef struct repet_params {
 int repet_create(int device, repet_handle** out);
 int repet_destroy(repet_handle* h);
 const char* repet_last_error(repet_handle* h);
-/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL restores the handle's own. */
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL restores the handle's own
+ * stream; pass cudaStreamLegacy ((void*)0x1) for the legacy default stream. */
 int repet_set_stream(repet_handle* h, void* cuda_stream);
 /* Analysis window, HOST pointer, n = window length (built with SciPy's periodic Hamming by the
  * host, repet.py:131 -- SciPy's values differ from the closed form by up to 1 ulp). */
@@ -82,6 +83,9 @@ const char* repet_version(void);
 #define REPET_K_MODEL 3
 #define REPET_K_MASK_ISTFT 4
 #define REPET_K_CONVERT 5
+/* Process-wide launch-shape knobs for experiments: "stft_minb", "mask_minb" (resident CTAs per SM
+ * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic). */
+int repet_set_tuning(const char* name, int value);
 int repet_set_profiling(repet_handle* h, int on);
 int repet_profile_read(repet_handle* h, double* ms, uint64_t* counts, int reset);
 const char* repet_kernel_name(int id);

@@ -26,8 +26,10 @@ constexpr int FFT_N = 2048;
 constexpr int FFT_THREADS = 128;
 constexpr int FFT_BUF = 16 * 129;  // float2 elements per exchange buffer (>= 2048)
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add/sub are one packed-fp32 instruction each on sm_100 (FADD2 / FFMA2): the two halves
+// of a float2 live in an aligned register pair.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -36,11 +38,12 @@ __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a
 
 // 4-point DFT, natural order in and out.
 __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
     a0 = cadd(t0, t2);
-    a1 = cadd(t1, t3);
     a2 = csub(t0, t2);
-    a3 = csub(t1, t3);
+    // t1 +- (-i d): the cross terms stay scalar (no half swap needed)
+    a1 = make_float2(t1.x + d.y, t1.y - d.x);
+    a3 = make_float2(t1.x - d.y, t1.y + d.x);
 }
 
 #define REPET_SQRT1_2 0.70710678118654752440f
@@ -146,8 +149,23 @@ __device__ __forceinline__ void fft_stage3(float2 (&r)[16], const float2* __rest
     }
 }
 
-// One magnitude definition for every kernel, so that |X| compares bit-identically wherever
-// it is recomputed (the model's min() against the mixture depends on it).
-__device__ __forceinline__ float cmag(float2 v) { return __fsqrt_rn(__fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y))); }
+// One squared-magnitude / magnitude definition for every kernel, so that |X| is bit-identical
+// wherever it is recomputed.  The square root is the hardware approximation (<= 2 ulp): the
+// magnitudes only feed medians, soft masks and the beat spectrum, all far above that error.
+__device__ __forceinline__ float cmag2(float2 v) { return __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)); }
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float cmag(float2 v) { return fast_sqrt(cmag2(v)); }
+
+// one 128-byte line towards L2, no register or scoreboard cost
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 }  // namespace repet

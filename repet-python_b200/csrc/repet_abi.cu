@@ -147,7 +147,9 @@ int plan_original(repet_handle* h, const repet_params* p, int n_channels, int64_
     plan->nch = n_channels;
     plan->lag_hi = lag_hi;
     plan->pmax = lag_hi;  // period = lag + 1 <= lag_hi
-    int want_parts = std::max(1, std::min(129, (h->sm_count * 6 + chunk_hint - 1) / std::max(1, chunk_hint)));
+    // measured on B200 (profiles/r1_sweeps.md): ~64 partitions of the 1025 rows per clip is the sweet spot
+    int want_parts = std::max(64, std::min(129, (h->sm_count * 6 + chunk_hint - 1) / std::max(1, chunk_hint)));
+    if (g_tuning.beat_parts > 0) want_parts = std::min(129, g_tuning.beat_parts);
     int f_per_part = ((NBIN + want_parts - 1) / want_parts + 7) / 8 * 8;
     plan->f_per_part = f_per_part;
     plan->n_parts = (NBIN + f_per_part - 1) / f_per_part;
@@ -163,12 +165,19 @@ int plan_original(repet_handle* h, const repet_params* p, int n_channels, int64_
 
 size_t default_ws_limit(repet_handle* h) {
     if (h->ws_limit) return (size_t)h->ws_limit;
-    return (size_t)6 << 30;
+    // big chunks win (launch tails and the per-clip period kernel amortise): up to 24 GB, but never
+    // more than 40 % of what is free on the device
+    size_t free_b = 0, total_b = 0;
+    size_t limit = (size_t)24 << 30;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        limit = std::min(limit, (size_t)((double)(free_b + h->arena_bytes) * 0.4));
+    return std::max(limit, (size_t)256 << 20);
 }
 
 int pick_frames_per_cta(repet_handle* h, long long total_frames) {
+    if (g_tuning.frames_per_cta > 0) return g_tuning.frames_per_cta;
     long long k = total_frames / ((long long)h->sm_count * 8);
-    return (int)std::max(4LL, std::min(32LL, k));
+    return (int)std::max(4LL, std::min(16LL, k));
 }
 
 // `original` on device-resident clips, in workspace-sized chunks.  `ws` is arena space after
@@ -333,6 +342,17 @@ int repet_synchronize(repet_handle* h) {
 }
 
 uint64_t repet_launch_count(repet_handle* h) { return h ? h->launches : 0; }
+
+int repet_set_tuning(const char* name, int value) {
+    if (!name) return REPET_E_INVALID_ARG;
+    const std::string key(name);
+    if (key == "stft_minb") g_tuning.stft_minb = value;
+    else if (key == "mask_minb") g_tuning.mask_minb = value;
+    else if (key == "frames_per_cta") g_tuning.frames_per_cta = value;
+    else if (key == "beat_parts") g_tuning.beat_parts = value;
+    else return REPET_E_INVALID_ARG;
+    return REPET_OK;
+}
 
 int repet_set_profiling(repet_handle* h, int on) {
     if (!h) return REPET_E_INVALID_ARG;

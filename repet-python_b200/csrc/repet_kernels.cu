@@ -10,11 +10,10 @@
 // medians, similar-frame medians) is a coalesced row read.
 #include "repet_kernels.cuh"
 #include "fft2048.cuh"
+#include "median_networks.cuh"
 
 namespace repet {
 
-// np.finfo(float).eps of the reference's soft mask (repet.py:1446); representable in fp32.
-#define REPET_EPS 2.220446049250313e-16f
 
 // ------------------------------------------------------------------------------------------
 // k_stft  --  _stft + abs + channel mean (+ square)      repet.py:1001-1060, 158, 162, 667
@@ -24,8 +23,8 @@ namespace repet {
 // (n = n1*128 + t), so the overlap is carried in registers: 16 new samples per thread-frame.
 // Algorithmic bytes per frame: 2*4 KB audio in, 16 KB X out, 4.1 KB P out.
 // ------------------------------------------------------------------------------------------
-template <int NCH>
-__global__ void __launch_bounds__(FFT_THREADS)
+template <int NCH, int MINB>
+__global__ void __launch_bounds__(FFT_THREADS, MINB)
 k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window, FftTables tb,
        float2* __restrict__ X, float* __restrict__ P, int pmode, int K) {
     __shared__ float2 s_buf[2][FFT_BUF];
@@ -52,6 +51,11 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
         float2 r[16];
         const long long base = (long long)(j - 1) * HOP + t;
         const bool carry = j > j0;
+        // pull the next frame's new half (2 x 4 KB) towards L2 while this frame is transformed
+        if (t < 64 && j + 1 < j1) {
+            const long long nxt = (long long)(j + 1) * HOP + (t & 31) * 32;
+            if (nxt < g.S) prefetch_l2((t < 32 || NCH == 1 ? a0 : a1) + nxt);
+        }
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
             float xl, xr = 0.f;
@@ -119,13 +123,20 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
     }
 }
 
+Tuning g_tuning;
+
 void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,
                  float* P, int pmode, int frames_per_cta) {
     dim3 grid((g.T + frames_per_cta - 1) / frames_per_cta, g.n_items);
-    if (nch == 2)
-        k_stft<2><<<grid, FFT_THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta);
-    else
-        k_stft<1><<<grid, FFT_THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta);
+#define REPET_GO(NCH, MINB) k_stft<NCH, MINB><<<grid, FFT_THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta)
+    if (nch == 2) {
+        if (g_tuning.stft_minb >= 6) REPET_GO(2, 6);
+        else if (g_tuning.stft_minb == 5) REPET_GO(2, 5);
+        else REPET_GO(2, 4);
+    } else {
+        REPET_GO(1, 4);
+    }
+#undef REPET_GO
 }
 
 // ------------------------------------------------------------------------------------------
@@ -227,7 +238,7 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
 // bin, and doing this single small transform in double keeps the fp32 front end's error out
 // of the argmax.  period = first argmax over lags [lo, hi) + 1 (quirks Q1, Q2).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double norm_rows, int lag_lo, int lag_hi,
           int out_lo, int out_hi, double* __restrict__ beat_out, int beat_pitch, int* __restrict__ period,
           double* __restrict__ stats) {
@@ -236,7 +247,7 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
     __shared__ double s_b[BEAT_L];
     const int t = threadIdx.x;
     const int bi = blockIdx.x;
-    for (int k = t; k < BEAT_L; k += 128) {
+    for (int k = t; k < BEAT_L; k += 256) {
         double a = 0.0;
         const float* __restrict__ src = psd_part + (size_t)bi * n_parts * BEAT_L + k;
         for (int part = 0; part < n_parts; ++part) a += (double)src[(size_t)part * BEAT_L];
@@ -244,14 +255,14 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
         s_cos[k] = cospi((double)k / (double)(BEAT_L / 2));
     }
     __syncthreads();
-    for (int k = t; k <= BEAT_L / 2; k += 128) s_psd[k] = 0.5 * (s_b[k] + s_b[(BEAT_L - k) & (BEAT_L - 1)]);
+    for (int k = t; k <= BEAT_L / 2; k += 256) s_psd[k] = 0.5 * (s_b[k] + s_b[(BEAT_L - k) & (BEAT_L - 1)]);
     __syncthreads();
     int l0 = out_lo, l1 = out_hi;
     if (period) {
         l0 = (out_hi > out_lo) ? min(out_lo, lag_lo) : lag_lo;
         l1 = (out_hi > out_lo) ? max(out_hi, lag_hi) : lag_hi;
     }
-    for (int l = l0 + t; l < l1; l += 128) {
+    for (int l = l0 + t; l < l1; l += 256) {
         double s = 0.0;
         for (int k = 1; k < BEAT_L / 2; ++k) s = fma(s_psd[k], s_cos[(k * l) & (BEAT_L - 1)], s);
         s = 2.0 * s + s_psd[0] + ((l & 1) ? -s_psd[BEAT_L / 2] : s_psd[BEAT_L / 2]);
@@ -259,7 +270,7 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
     }
     __syncthreads();
     if (beat_out)
-        for (int l = out_lo + t; l < out_hi; l += 128) beat_out[(size_t)bi * beat_pitch + (l - out_lo)] = s_b[l];
+        for (int l = out_lo + t; l < out_hi; l += 256) beat_out[(size_t)bi * beat_pitch + (l - out_lo)] = s_b[l];
     if (period && t == 0) {
         double best = s_b[lag_lo], second = -1.0e300;
         int arg = lag_lo, arg2 = -1;
@@ -288,46 +299,59 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
 void launch_periods(cudaStream_t st, const float* psd_part, int n_beat_items, int n_parts, int t_len, double norm_rows,
                     int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out, int beat_pitch, int* period,
                     double* stats) {
-    k_periods<<<n_beat_items, 128, 0, st>>>(psd_part, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo, out_hi,
+    k_periods<<<n_beat_items, 256, 0, st>>>(psd_part, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo, out_hi,
                                             beat_out, beat_pitch, period, stats);
 }
 
 // ------------------------------------------------------------------------------------------
-// Median of n <= NP values held in registers: pad with -inf below and +inf above so that the
-// median always sits at sorted positions NP/2-1 (odd n) or NP/2-1, NP/2 (even n: mean of the
-// two middle values, as np.median does), then run a bitonic network with static indices.
+// Medians.  Magnitudes are compared through their SQUARES (monotonic), so a median costs one
+// or two square roots instead of n.  For n <= 32 the values sit in registers and go through a
+// generated selection network (median_networks.cuh: pruned odd-even merge sort, only the
+// half-comparators that reach the middle outputs).  np.median's even-count rule (mean of the two
+// middle values) applies to the magnitudes, i.e. after the square roots.
 // ------------------------------------------------------------------------------------------
-template <int NP>
-__device__ __forceinline__ float median_network(float (&v)[NP], int n) {
-#pragma unroll
-    for (int k = 2; k <= NP; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const float lo = fminf(v[i], v[l]), hi = fmaxf(v[i], v[l]);
-                    if ((i & k) == 0) {
-                        v[i] = lo;
-                        v[l] = hi;
-                    } else {
-                        v[i] = hi;
-                        v[l] = lo;
-                    }
-                }
-            }
-        }
+// squared magnitude of bin k (0..1024) of one (frame, channel) row of X; bin 0 packs (DC, Nyquist)
+__device__ __forceinline__ float row_mag2(const float2* __restrict__ row, int k) {
+    if (k == 0) {
+        const float x = __ldg(&row[0]).x;
+        return __fmul_rn(x, x);
     }
-    return (n & 1) ? v[NP / 2 - 1] : 0.5f * (v[NP / 2 - 1] + v[NP / 2]);
+    if (k == XPITCH) {
+        const float y = __ldg(&row[0]).y;
+        return __fmul_rn(y, y);
+    }
+    return cmag2(__ldg(&row[k]));
 }
 
-// value to load into slot s of an NP-wide network holding n real values: slots
-// [lo_pad, lo_pad + n) are data, below -inf, above +inf
-__device__ __forceinline__ int median_lo_pad(int NP, int n) { return (NP - n) >> 1; }
+// median of the magnitudes of two adjacent bins (k, k+1) over N frames `stride` apart, one
+// 16-byte load per frame.  first_is_dc: bin k = 0 holds (DC.re, Nyquist.re); only DC is used here.
+template <int N>
+__device__ __forceinline__ float2 strided_median_pair(const float2* __restrict__ base, size_t stride, bool first_is_dc) {
+    float v0[N], v1[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(base + (size_t)s * stride));
+        v0[s] = first_is_dc ? __fmul_rn(x.x, x.x) : __fmaf_rn(x.x, x.x, __fmul_rn(x.y, x.y));
+        v1[s] = __fmaf_rn(x.z, x.z, __fmul_rn(x.w, x.w));
+    }
+    median_select<N>(v0);
+    median_select<N>(v1);
+    if (N & 1) return make_float2(fast_sqrt(v0[(N - 1) / 2]), fast_sqrt(v1[(N - 1) / 2]));
+    return make_float2(0.5f * (fast_sqrt(v0[(N - 1) / 2]) + fast_sqrt(v0[N / 2])),
+                       0.5f * (fast_sqrt(v1[(N - 1) / 2]) + fast_sqrt(v1[N / 2])));
+}
+
+template <int N>
+__device__ __forceinline__ float strided_median(const float2* __restrict__ base, size_t stride, int k) {
+    float v[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) v[s] = row_mag2(base + (size_t)s * stride, k);
+    median_select<N>(v);
+    return (N & 1) ? fast_sqrt(v[(N - 1) / 2]) : 0.5f * (fast_sqrt(v[(N - 1) / 2]) + fast_sqrt(v[N / 2]));
+}
 
 // Fallback for n > 32: rank selection straight from memory (O(n^2), exact).  `fetch(s)` returns
-// value s.  Returns the median with np.median's even-count rule.
+// squared magnitude s.
 template <typename Fetch>
 __device__ float median_by_rank(int n, Fetch fetch) {
     const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
@@ -350,75 +374,98 @@ __device__ float median_by_rank(int n, Fetch fetch) {
             got_hi = true;
         }
     }
-    return 0.5f * (v_lo + v_hi);
-}
-
-// magnitude of bin k (0..1024) of one (frame, channel) row of X; bin 0 packs (DC, Nyquist)
-__device__ __forceinline__ float row_mag(const float2* __restrict__ row, int k) {
-    if (k == 0) return fabsf(__ldg(&row[0]).x);
-    if (k == XPITCH) return fabsf(__ldg(&row[0]).y);
-    return cmag(__ldg(&row[k]));
-}
-
-template <int NP>
-__device__ __forceinline__ float strided_median(const float2* __restrict__ base, size_t stride, int n, int k) {
-    float v[NP];
-    const int lo = median_lo_pad(NP, n);
-#pragma unroll
-    for (int s = 0; s < NP; ++s) {
-        const int d = s - lo;
-        v[s] = d < 0 ? -INFINITY : (d < n ? row_mag(base + (size_t)d * stride, k) : INFINITY);
-    }
-    return median_network<NP>(v, n);
+    return 0.5f * (fast_sqrt(v_lo) + fast_sqrt(v_hi));
 }
 
 // ------------------------------------------------------------------------------------------
 // k_model  --  the repeating segment of _mask                      repet.py:1398-1438
 // model[f, q] = median over s of V[f, s*p + q]; r = ceil(T/p) values for phases
 // q < T-(r-1)p, r-1 otherwise (the reference's zero padding is excluded, quirk Q9).
-// Grid (9 bin blocks, pmax phases, items*channels); CTAs of phases q >= p[item] exit.
-// Threads run along bins, so each of the n gathers is a coalesced row read of X.
+// Grid (phase groups + 1, items*channels).  A CTA of 128 threads owns MODEL_QB consecutive
+// phases of one (item, channel); each thread takes bin PAIRS (16-byte loads) in 4 passes of 256
+// bins, so every gather is a coalesced 2 KB row segment and a thread keeps 2n loads in flight.
+// The extra CTA column does the Nyquist bin (packed in bin 0's imaginary slot), one phase per
+// thread.  Algorithmic bytes: X read once.
 // ------------------------------------------------------------------------------------------
+constexpr int MODEL_QB = 8;
+
+template <int N>
+__device__ __forceinline__ void model_phase(const float2* __restrict__ base, size_t stride, float* __restrict__ out, int t) {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int k = 2 * (t + 128 * i);
+        const float2 m = strided_median_pair<N>(base + k, stride, k == 0);
+        *reinterpret_cast<float2*>(out + k) = m;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_model(const float2* __restrict__ X, int T, int nch, const int* __restrict__ period, int pmax,
-        float* __restrict__ model) {
-    const int item = blockIdx.z / nch, c = blockIdx.z - item * nch;
+        float* __restrict__ model, int n_groups) {
+    const int item = blockIdx.y / nch, c = blockIdx.y - item * nch;
     const int p = period[item];
-    const int q = blockIdx.y;
-    if (q >= p || p <= 0) return;
-    const int k = blockIdx.x * 128 + threadIdx.x;
-    if (k > XPITCH) return;
+    if (p <= 0) return;
+    const int t = threadIdx.x;
     const int r = (T + p - 1) / p;
     const int k0 = T - (r - 1) * p;
-    const int n = q < k0 ? r : r - 1;
     const size_t stride = (size_t)p * nch * XPITCH;
-    const float2* __restrict__ base = X + ((size_t)item * T + q) * (size_t)(nch * XPITCH) + (size_t)c * XPITCH;
-    float med;
-    if (n <= 0)
-        med = nanf("");
-    else if (n <= 4)
-        med = strided_median<4>(base, stride, n, k);
-    else if (n <= 8)
-        med = strided_median<8>(base, stride, n, k);
-    else if (n <= 16)
-        med = strided_median<16>(base, stride, n, k);
-    else if (n <= 32)
-        med = strided_median<32>(base, stride, n, k);
-    else
-        med = median_by_rank(n, [&](int s) { return row_mag(base + (size_t)s * stride, k); });
-    model[(((size_t)item * nch + c) * pmax + q) * PPITCH + k] = med;
+    const float2* __restrict__ chan = X + (size_t)item * T * (size_t)(nch * XPITCH) + (size_t)c * XPITCH;
+    float* __restrict__ mrow = model + ((size_t)item * nch + c) * (size_t)pmax * PPITCH;
+    if ((int)blockIdx.x == n_groups) {
+        // Nyquist bins of every phase
+        for (int q = t; q < p; q += 128) {
+            const int n = q < k0 ? r : r - 1;
+            const float2* __restrict__ base = chan + (size_t)q * (nch * XPITCH);
+            float med;
+            switch (n) {
+#define REPET_CASE(N) case N: med = strided_median<N>(base, stride, XPITCH); break;
+                REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+                REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+                REPET_CASE(15) REPET_CASE(16) REPET_CASE(17) REPET_CASE(18) REPET_CASE(19) REPET_CASE(20) REPET_CASE(21)
+                REPET_CASE(22) REPET_CASE(23) REPET_CASE(24) REPET_CASE(25) REPET_CASE(26) REPET_CASE(27) REPET_CASE(28)
+                REPET_CASE(29) REPET_CASE(30) REPET_CASE(31) REPET_CASE(32)
+#undef REPET_CASE
+                default:
+                    med = n <= 0 ? nanf("")
+                                 : median_by_rank(n, [&](int s) { return row_mag2(base + (size_t)s * stride, XPITCH); });
+            }
+            mrow[(size_t)q * PPITCH + XPITCH] = med;
+        }
+        return;
+    }
+    const int q_end = min(p, ((int)blockIdx.x + 1) * MODEL_QB);
+    for (int q = blockIdx.x * MODEL_QB; q < q_end; ++q) {
+        const int n = q < k0 ? r : r - 1;
+        const float2* __restrict__ base = chan + (size_t)q * (nch * XPITCH);
+        float* __restrict__ out = mrow + (size_t)q * PPITCH;
+        switch (n) {
+#define REPET_CASE(N) case N: model_phase<N>(base, stride, out, t); break;
+            REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+            REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+            REPET_CASE(15) REPET_CASE(16) REPET_CASE(17) REPET_CASE(18) REPET_CASE(19) REPET_CASE(20) REPET_CASE(21)
+            REPET_CASE(22) REPET_CASE(23) REPET_CASE(24) REPET_CASE(25) REPET_CASE(26) REPET_CASE(27) REPET_CASE(28)
+            REPET_CASE(29) REPET_CASE(30) REPET_CASE(31) REPET_CASE(32)
+#undef REPET_CASE
+            default:
+                for (int k = t; k < XPITCH; k += 128)
+                    out[k] = n <= 0 ? nanf("")
+                                    : median_by_rank(n, [&](int s) { return row_mag2(base + (size_t)s * stride, k); });
+        }
+    }
 }
 
 void launch_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
                   float* model) {
-    dim3 grid(9, pmax, n_items * nch);
-    k_model<<<grid, 128, 0, st>>>(X, T, nch, period, pmax, model);
+    const int n_groups = (pmax + MODEL_QB - 1) / MODEL_QB;
+    dim3 grid(n_groups + 1, n_items * nch);
+    k_model<<<grid, 128, 0, st>>>(X, T, nch, period, pmax, model, n_groups);
 }
 
-// soft mask of one bin: min with the mixture, (W+eps)/(V+eps)     repet.py:1441-1448 (quirk Q10)
-__device__ __forceinline__ float soft_mask(float model, float v) {
-    return __fdiv_rn(fminf(model, v) + REPET_EPS, v + REPET_EPS);
-}
+// Soft mask of one bin: (min(model, V) + eps) / (V + eps)          repet.py:1441-1448 (quirk Q10)
+// computed from the squared magnitude as min(model * rsqrt(V^2), 1): no square root, no division.
+// V = 0 gives model * inf = inf (or NaN for model = 0), and fminf(., 1) returns 1 -- the
+// reference's eps/eps.  For model = 0 < V the reference's eps/(V+eps) ~ 1e-16/V becomes 0.
+__device__ __forceinline__ float soft_mask(float model, float v2) { return fminf(model * fast_rsqrt(v2), 1.0f); }
 
 // ------------------------------------------------------------------------------------------
 // k_mask_istft  --  rest of _mask + high-pass + mirror + apply + _istft
@@ -432,8 +479,8 @@ __device__ __forceinline__ float soft_mask(float model, float v) {
 // MASKED = false is the plain _istft helper.
 // Algorithmic bytes per frame: 16 KB X in, 8 KB audio out (+ model rows, L2 resident).
 // ------------------------------------------------------------------------------------------
-template <int NCH, bool MASKED>
-__global__ void __launch_bounds__(FFT_THREADS)
+template <int NCH, bool MASKED, int MINB>
+__global__ void __launch_bounds__(FFT_THREADS, MINB)
 k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ period, int pmax,
              const float* __restrict__ model, int cutoff, float scale, FftTables tb, float* __restrict__ out,
              int nblk) {
@@ -468,6 +515,8 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             ml_row = model + (((size_t)item * NCH + 0) * pmax + q) * PPITCH;
             mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
         }
+        // pull the next frame's spectra (NCH x 8 KB) towards L2 while this frame is processed
+        if (j < b1 && t < 64 * NCH) prefetch_l2(xl_row + (size_t)(NCH * XPITCH) + t * 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int k = t + 128 * i;
@@ -478,11 +527,11 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
                 // DC (mask kept, quirk Q11) and Nyquist, both purely real
                 float m_dc_l = 1.f, m_ny_l = 1.f, m_dc_r = 1.f, m_ny_r = 1.f;
                 if (MASKED) {
-                    m_dc_l = soft_mask(__ldg(&ml_row[0]), fabsf(xl.x));
-                    m_ny_l = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&ml_row[XPITCH]), fabsf(xl.y));
+                    m_dc_l = soft_mask(__ldg(&ml_row[0]), xl.x * xl.x);
+                    m_ny_l = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&ml_row[XPITCH]), xl.y * xl.y);
                     if (NCH == 2) {
-                        m_dc_r = soft_mask(__ldg(&mr_row[0]), fabsf(xr.x));
-                        m_ny_r = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&mr_row[XPITCH]), fabsf(xr.y));
+                        m_dc_r = soft_mask(__ldg(&mr_row[0]), xr.x * xr.x);
+                        m_ny_r = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&mr_row[XPITCH]), xr.y * xr.y);
                     }
                 }
                 // swapped storage: (im, re) of Z = YL + i YR
@@ -492,8 +541,8 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
                 float m_l = 1.f, m_r = 1.f;
                 if (MASKED) {
                     if (k > cutoff) {
-                        m_l = soft_mask(__ldg(&ml_row[k]), cmag(xl));
-                        if (NCH == 2) m_r = soft_mask(__ldg(&mr_row[k]), cmag(xr));
+                        m_l = soft_mask(__ldg(&ml_row[k]), cmag2(xl));
+                        if (NCH == 2) m_r = soft_mask(__ldg(&mr_row[k]), cmag2(xr));
                     }
                 }
                 const float2 yl = make_float2(m_l * xl.x, m_l * xl.y);
@@ -541,10 +590,16 @@ void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const 
                        const float* model, int cutoff, float scale, FftTables tb, float* out, int blocks_per_cta) {
     const int nblocks = g.T - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
-    if (nch == 2)
-        k_mask_istft<2, true><<<grid, FFT_THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta);
-    else
-        k_mask_istft<1, true><<<grid, FFT_THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta);
+#define REPET_GO(NCH, MINB) \
+    k_mask_istft<NCH, true, MINB><<<grid, FFT_THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
+    if (nch == 2) {
+        if (g_tuning.mask_minb >= 6) REPET_GO(2, 6);
+        else if (g_tuning.mask_minb == 5) REPET_GO(2, 5);
+        else REPET_GO(2, 4);
+    } else {
+        REPET_GO(1, 4);
+    }
+#undef REPET_GO
 }
 
 void launch_istft(cudaStream_t st, const float2* X, Geom g, int nch, float scale, FftTables tb, float* out,
@@ -552,9 +607,9 @@ void launch_istft(cudaStream_t st, const float2* X, Geom g, int nch, float scale
     const int nblocks = g.T - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
     if (nch == 2)
-        k_mask_istft<2, false><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
+        k_mask_istft<2, false, 4><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
     else
-        k_mask_istft<1, false><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
+        k_mask_istft<1, false, 4><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -570,7 +625,7 @@ k_mask_only(const float2* __restrict__ X, int T, int nch, const int* __restrict_
     const int p = period[item];
     const float2* __restrict__ row = X + ((size_t)item * T + j) * (size_t)(nch * XPITCH) + (size_t)c * XPITCH;
     const float m = model[(((size_t)item * nch + c) * pmax + (j % p)) * PPITCH + k];
-    mask_out[(((size_t)item * nch + c) * T + j) * PPITCH + k] = soft_mask(m, row_mag(row, k));
+    mask_out[(((size_t)item * nch + c) * T + j) * PPITCH + k] = soft_mask(m, row_mag2(row, k));
 }
 
 void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,

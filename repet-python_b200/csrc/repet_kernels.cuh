@@ -34,6 +34,15 @@ struct FftTables {
 
 enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2 };
 
+// Launch-shape knobs (repet_set_tuning); defaults are the measured best on B200.
+struct Tuning {
+    int stft_minb = 4;       // resident CTAs per SM the STFT kernel is compiled for (4, 5, 6)
+    int mask_minb = 5;       // same for the mask+ISTFT kernel
+    int frames_per_cta = 0;  // 0 = pick from the batch size
+    int beat_parts = 0;      // 0 = pick from the batch size
+};
+extern Tuning g_tuning;
+
 // k_stft: audio -> X (half spectra, both channels) [+ P = (mean_c |X|)^2 or mean_c |X|]
 void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,
                  float* P, int pmode, int frames_per_cta);

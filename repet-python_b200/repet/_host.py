@@ -66,6 +66,7 @@ SIGNATURES = {
     "repet_set_workspace_limit": (_c_int, [_vp, _c_u64]),
     "repet_synchronize": (_c_int, [_vp]),
     "repet_launch_count": (_c_u64, [_vp]),
+    "repet_set_tuning": (_c_int, [ctypes.c_char_p, _c_int]),
     "repet_set_profiling": (_c_int, [_vp, _c_int]),
     "repet_profile_read": (_c_int, [_vp, _vp, _vp, _c_int]),
     "repet_kernel_name": (ctypes.c_char_p, [_c_int]),
@@ -158,7 +159,14 @@ class Handle:
             self.set_window(hamming_window(window_length), key=("hamming", window_length))
 
     def set_stream(self, cuda_stream_pointer):
-        self.check(self.lib.repet_set_stream(self.h, _vp(cuda_stream_pointer) if cuda_stream_pointer else None))
+        """Enqueue on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream).
+        None restores the handle's own stream; 0 means the legacy default stream, which the
+        runtime spells cudaStreamLegacy = 0x1."""
+        if cuda_stream_pointer is None:
+            pointer = None
+        else:
+            pointer = _vp(int(cuda_stream_pointer) or 1)
+        self.check(self.lib.repet_set_stream(self.h, pointer))
 
     def set_workspace_limit(self, number_bytes):
         self.check(self.lib.repet_set_workspace_limit(self.h, int(number_bytes)))
@@ -180,6 +188,14 @@ class Handle:
         return {
             self.lib.repet_kernel_name(i).decode(): (float(ms[i]), int(counts[i])) for i in range(8) if counts[i]
         }
+
+
+def set_tuning(**knobs):
+    """Process-wide launch-shape knobs (see repet_set_tuning in include/repet_b200.h)."""
+    lib = load_library()
+    for name, value in knobs.items():
+        if lib.repet_set_tuning(name.encode(), int(value)) != REPET_OK:
+            raise ValueError("unknown tuning knob %r" % name)
 
 
 _handles = {}
