@@ -83,6 +83,7 @@ const char* repet_version(void);
 #define REPET_K_MODEL 3
 #define REPET_K_MASK_ISTFT 4
 #define REPET_K_CONVERT 5
+#define REPET_K_XFADE 6
 /* Process-wide launch-shape knobs for experiments: "stft_minb", "mask_minb" (resident CTAs per SM
  * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic). */
 int repet_set_tuning(const char* name, int value);
@@ -105,6 +106,27 @@ int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n
 int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels,
                        const repet_params* p, double* background, int32_t* period_host);
 
+/* repet.extended (repet.py:205-419): `original` on 10 s segments every 5 s with a triangular
+ * cross-fade.  p->segment_length / segment_step are in SAMPLES.  Integer output: the period of
+ * every segment, [n_clips][repet_extended_segments(p, n_samples)]. */
+int repet_extended_segments(const repet_params* p, int64_t n_samples);
+int repet_extended_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host);
+int repet_extended_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                         const repet_params* p, float* background, int32_t* periods_host);
+int repet_extended_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                       double* background, int32_t* periods_host, int periods_capacity);
+
+/* repet.adaptive (repet.py:422-568): sliding beat spectrogram, per-frame periods, per-frame
+ * median over <= filter_order period-offset frames.  p->segment_length / segment_step are in
+ * FRAMES.  Integer output: the period of every frame, [n_clips][n_frames]. */
+int repet_adaptive_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host);
+int repet_adaptive_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                         const repet_params* p, float* background, int32_t* periods_host);
+int repet_adaptive_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                       double* background, int32_t* periods_host, int periods_capacity);
+
 /* ---- helpers (unit parity with the reference's private functions), HOST pointers -------- */
 /* _stft (repet.py:1001-1060) of n_channels (1 or 2) real signals at once.
  * signal: [n_channels][n_samples] fp32; spectrum: [n_frames][n_channels][N/2] float2 with
@@ -124,6 +146,19 @@ int repet_period(repet_handle* h, const float* spectrogram, int n_frames, int n_
 /* _mask (repet.py:1386-1458): magnitude spectrogram [n_frames][1025] fp32 + period ->
  * mask [n_frames][1025] fp32. */
 int repet_mask(repet_handle* h, const float* magnitude, int n_frames, int period, float* mask);
+
+/* _adaptivemask (repet.py:1461-1508): magnitudes [n_frames][1025], per-frame periods, order ->
+ * mask [n_frames][1025]. */
+int repet_adaptivemask(repet_handle* h, const float* magnitude, int n_frames, const int32_t* periods, int filter_order,
+                       float* mask);
+/* _beatspectrogram (repet.py:1161-1206) before the column replication: the beat spectrum of
+ * every segment i = 0, step, 2 step, ... -> beat[n_segments][segment_length] float64. */
+int repet_beatspectrogram(repet_handle* h, const float* spectrogram, int n_frames, int n_rows, int segment_length,
+                          int segment_step, double* beat, int32_t* n_segments_out);
+/* _periods (repet.py:1249-1291) on a caller-provided beat spectrum (n_columns = 1) or beat
+ * spectrogram, beat[n_lags][n_columns] row-major float64 -> periods[n_columns]. */
+int repet_periods(repet_handle* h, const double* beat, int n_lags, int n_columns, int period_lo, int period_hi,
+                  int32_t* periods);
 
 #ifdef __cplusplus
 }

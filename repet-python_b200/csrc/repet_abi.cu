@@ -1,104 +1,25 @@
-// C ABI of librepet_b200.so (declared in include/repet_b200.h): handle, workspace arena,
-// transform tables, chunked batch drivers and the helper-level entry points.
-#include "../../include/repet_b200.h"
-#include "repet_kernels.cuh"
+// C ABI of librepet_b200.so (declared in include/repet_b200.h): handle lifetime, workspace arena,
+// transform tables, profiling, and the helper-level entry points.  The batch drivers live in
+// repet_drivers.cu.
+#include "repet_internal.h"
 
-#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <string>
-#include <vector>
 
 using namespace repet;
-
-struct repet_handle {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t h2d_stream = nullptr;
-    cudaStream_t d2h_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
-    cudaEvent_t ev_compute[2] = {nullptr, nullptr};
-    cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
-    std::string err;
-    float2* tw1 = nullptr;
-    float2* tw2 = nullptr;
-    float* window = nullptr;
-    int window_n = 0;
-    double window_gain = 0.0;  // sum(window[0:N:H])
-    unsigned char* arena = nullptr;
-    size_t arena_bytes = 0;
-    uint64_t ws_limit = 0;
-    uint64_t launches = 0;
-    int sm_count = 148;
-    // optional per-kernel timing (bench.py's roofline): one event pair per launch
-    bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;
-    std::vector<int> prof_ids;
-    size_t prof_used = 0;
-    double prof_ms[REPET_NUM_KERNELS] = {0};
-    uint64_t prof_count[REPET_NUM_KERNELS] = {0};
-};
 
 namespace {
 
 const double kPi = 3.14159265358979323846264338327950288;
 const int FFT_N_HOST = 2048;
-const int MAX_ITEMS_PER_LAUNCH = 16384;  // grid.y / grid.z stay far below 65535
-
-int fail(repet_handle* h, int code, const std::string& msg) {
-    if (h) h->err = msg;
-    return code;
-}
-
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess)                                                                    \
-            return fail(h, e__ == cudaErrorMemoryAllocation ? REPET_E_OOM : REPET_E_CUDA,          \
-                        std::string(#call) + ": " + cudaGetErrorString(e__));                      \
-    } while (0)
-
-size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 const char* kKernelNames[REPET_NUM_KERNELS] = {"k_stft", "k_beat", "k_periods", "k_model", "k_mask_istft",
-                                               "k_convert", "k_other6", "k_other7"};
+                                               "k_convert", "k_xfade", "k_other7"};
 
-// Brackets one launch with an event pair when profiling is on; always counts the launch.
-struct Timed {
-    repet_handle* h;
-    Timed(repet_handle* handle, int id) : h(handle) {
-        h->launches += 1;
-        if (!h->profiling) return;
-        if (h->prof_used + 2 > h->prof_events.size()) {
-            for (int i = 0; i < 2; ++i) {
-                cudaEvent_t e = nullptr;
-                cudaEventCreate(&e);
-                h->prof_events.push_back(e);
-            }
-        }
-        h->prof_ids.push_back(id);
-        cudaEventRecord(h->prof_events[h->prof_used], h->stream);
-    }
-    ~Timed() {
-        if (!h->profiling) return;
-        cudaEventRecord(h->prof_events[h->prof_used + 1], h->stream);
-        h->prof_used += 2;
-    }
-};
+}  // namespace
 
-struct Bump {
-    unsigned char* base;
-    size_t off = 0;
-    explicit Bump(unsigned char* b) : base(b) {}
-    template <typename T>
-    T* take(size_t count) {
-        T* p = reinterpret_cast<T*>(base + off);
-        off = align_up(off + count * sizeof(T));
-        return p;
-    }
-};
+namespace repet {
 
 int ensure_arena(repet_handle* h, size_t bytes) {
     if (bytes <= h->arena_bytes) return REPET_OK;
@@ -111,12 +32,6 @@ int ensure_arena(repet_handle* h, size_t bytes) {
     return REPET_OK;
 }
 
-int frames_of(int64_t n_samples) {  // repet.py:1018-1028 with N = 2H
-    return (int)((n_samples + HOP - 1) / HOP) + 1;
-}
-
-FftTables tables(repet_handle* h) { return FftTables{h->tw1, h->tw2}; }
-
 int check_common(repet_handle* h, const repet_params* p, int n_channels) {
     if (!h) return REPET_E_INVALID_ARG;
     if (!p) return fail(h, REPET_E_INVALID_ARG, "params is null");
@@ -126,40 +41,6 @@ int check_common(repet_handle* h, const repet_params* p, int n_channels) {
     if (n_channels < 1 || n_channels > 2)
         return fail(h, REPET_E_UNSUPPORTED, "1 or 2 channels supported");
     if (h->window_n != WIN_N) return fail(h, REPET_E_INVALID_ARG, "repet_set_window has not been called");
-    return REPET_OK;
-}
-
-// per-item workspace of the `original` pipeline
-struct OriginalPlan {
-    int T, nch, pmax, lag_hi, n_parts, f_per_part;
-    size_t bytes_per_item;
-};
-
-int plan_original(repet_handle* h, const repet_params* p, int n_channels, int64_t n_samples, int chunk_hint,
-                  OriginalPlan* plan) {
-    const int T = frames_of(n_samples);
-    const int lag_hi = std::min(p->period_hi, T / 3);  // repet.py:1265-1267 (quirk Q2)
-    if (p->period_lo < 0 || lag_hi <= p->period_lo)
-        return fail(h, REPET_E_TOO_SHORT, "attempt to get argmax of an empty sequence (clip too short for the period range)");
-    if (T + lag_hi - 1 > BEAT_L)
-        return fail(h, REPET_E_UNSUPPORTED, "clip longer than the single-block beat transform (T + max lag > 2048 frames)");
-    plan->T = T;
-    plan->nch = n_channels;
-    plan->lag_hi = lag_hi;
-    plan->pmax = lag_hi;  // period = lag + 1 <= lag_hi
-    // measured on B200 (profiles/r1_sweeps.md): ~64 partitions of the 1025 rows per clip is the sweet spot
-    int want_parts = std::max(64, std::min(129, (h->sm_count * 6 + chunk_hint - 1) / std::max(1, chunk_hint)));
-    if (g_tuning.beat_parts > 0) want_parts = std::min(129, g_tuning.beat_parts);
-    int f_per_part = ((NBIN + want_parts - 1) / want_parts + 7) / 8 * 8;
-    plan->f_per_part = f_per_part;
-    plan->n_parts = (NBIN + f_per_part - 1) / f_per_part;
-    size_t b = 0;
-    b += align_up((size_t)T * n_channels * XPITCH * sizeof(float2));
-    b += align_up((size_t)T * PPITCH * sizeof(float));
-    b += align_up((size_t)plan->n_parts * BEAT_L * sizeof(float));
-    b += align_up((size_t)n_channels * plan->pmax * PPITCH * sizeof(float));
-    b += 512;
-    plan->bytes_per_item = b;
     return REPET_OK;
 }
 
@@ -174,66 +55,7 @@ size_t default_ws_limit(repet_handle* h) {
     return std::max(limit, (size_t)256 << 20);
 }
 
-int pick_frames_per_cta(repet_handle* h, long long total_frames) {
-    if (g_tuning.frames_per_cta > 0) return g_tuning.frames_per_cta;
-    long long k = total_frames / ((long long)h->sm_count * 8);
-    return (int)std::max(4LL, std::min(16LL, k));
-}
-
-// `original` on device-resident clips, in workspace-sized chunks.  `ws` is arena space after
-// whatever the caller reserved.
-int original_dev_chunked(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                         const repet_params* p, float* background, int32_t* periods_dev, unsigned char* ws,
-                         size_t ws_bytes, const OriginalPlan& plan) {
-    const int G = (int)std::min<size_t>(std::min<size_t>((size_t)n_clips, MAX_ITEMS_PER_LAUNCH),
-                                        std::max<size_t>(1, ws_bytes / plan.bytes_per_item));
-    const float scale = (float)(1.0 / ((double)WIN_N * p->cola_gain));
-    cudaStream_t st = h->stream;
-    for (int first = 0; first < n_clips; first += G) {
-        const int g_items = std::min(G, n_clips - first);
-        Bump bump(ws);
-        float2* X = bump.take<float2>((size_t)g_items * plan.T * n_channels * XPITCH);
-        float* P = bump.take<float>((size_t)g_items * plan.T * PPITCH);
-        float* psd = bump.take<float>((size_t)g_items * plan.n_parts * BEAT_L);
-        float* model = bump.take<float>((size_t)g_items * n_channels * plan.pmax * PPITCH);
-        Geom g;
-        g.n_items = g_items;
-        g.seg_per_clip = 1;
-        g.clip_stride = (long long)n_channels * n_samples;
-        g.seg_stride = 0;
-        g.chan_stride = n_samples;
-        g.first_offset = (long long)first * g.clip_stride;
-        g.S = (int)n_samples;
-        g.T = plan.T;
-        const int K = pick_frames_per_cta(h, (long long)g_items * plan.T);
-        {
-            Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, g, n_channels, h->window, tables(h), X, P, P_POWER, K);
-        }
-        {
-            Timed timed(h, REPET_K_BEAT);
-            launch_beat(st, P, g_items, plan.T, 0, plan.T, 0, 1, tables(h), psd, plan.n_parts, plan.f_per_part);
-        }
-        {
-            Timed timed(h, REPET_K_PERIODS);
-            launch_periods(st, psd, g_items, plan.n_parts, plan.T, (double)NBIN, p->period_lo, plan.lag_hi, 0, 0,
-                           nullptr, 0, periods_dev + first, nullptr);
-        }
-        {
-            Timed timed(h, REPET_K_MODEL);
-            launch_model(st, X, g_items, plan.T, n_channels, periods_dev + first, plan.pmax, model);
-        }
-        {
-            Timed timed(h, REPET_K_MASK_ISTFT);
-            launch_mask_istft(st, X, g, n_channels, periods_dev + first, plan.pmax, model, p->cutoff_bins, scale,
-                              tables(h), background, K);
-        }
-    }
-    CU(cudaGetLastError());
-    return REPET_OK;
-}
-
-}  // namespace
+}  // namespace repet
 
 extern "C" {
 
@@ -387,127 +209,6 @@ int repet_profile_read(repet_handle* h, double* ms, uint64_t* counts, int reset)
 const char* repet_kernel_name(int id) { return (id >= 0 && id < REPET_NUM_KERNELS) ? kKernelNames[id] : ""; }
 
 // ---------------------------------------------------------------------------------------------
-// drivers
-// ---------------------------------------------------------------------------------------------
-int repet_original_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
-    int rc = check_common(h, p, n_channels);
-    if (rc) return rc;
-    if (!audio || !background || n_clips < 0 || n_samples < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
-    if (n_clips == 0) return REPET_OK;
-    CU(cudaSetDevice(h->device));
-    OriginalPlan plan;
-    const size_t limit = default_ws_limit(h);
-    // size the chunk first with a neutral hint, then re-plan the beat partition for it
-    if ((rc = plan_original(h, p, n_channels, n_samples, 64, &plan))) return rc;
-    int G = (int)std::min<size_t>((size_t)n_clips, std::max<size_t>(1, limit / plan.bytes_per_item));
-    if ((rc = plan_original(h, p, n_channels, n_samples, G, &plan))) return rc;
-    G = (int)std::min<size_t>((size_t)n_clips, std::max<size_t>(1, limit / plan.bytes_per_item));
-    const size_t periods_bytes = periods_dev ? 0 : align_up((size_t)n_clips * sizeof(int32_t));
-    const size_t need = periods_bytes + (size_t)G * plan.bytes_per_item;
-    if ((rc = ensure_arena(h, need))) return rc;
-    int32_t* per = periods_dev ? periods_dev : reinterpret_cast<int32_t*>(h->arena);
-    rc = original_dev_chunked(h, audio, n_clips, n_channels, n_samples, p, background, per, h->arena + periods_bytes,
-                              (size_t)G * plan.bytes_per_item, plan);
-    if (rc) return rc;
-    if (periods_host) {
-        CU(cudaMemcpyAsync(periods_host, per, (size_t)n_clips * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-    }
-    return REPET_OK;
-}
-
-int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                         const repet_params* p, float* background, int32_t* periods_host) {
-    int rc = check_common(h, p, n_channels);
-    if (rc) return rc;
-    if (!audio || !background || n_clips < 0 || n_samples < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
-    if (n_clips == 0) return REPET_OK;
-    CU(cudaSetDevice(h->device));
-    const size_t clip_elems = (size_t)n_channels * (size_t)n_samples;
-    const size_t clip_bytes = clip_elems * sizeof(float);
-    // copy granularity: about 256 MB per slot, two slots in flight
-    int Gc = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_clips, ((size_t)256 << 20) / std::max<size_t>(1, clip_bytes)));
-    OriginalPlan plan;
-    if ((rc = plan_original(h, p, n_channels, n_samples, Gc, &plan))) return rc;
-    const size_t limit = default_ws_limit(h);
-    const int Gw = (int)std::min<size_t>((size_t)Gc, std::max<size_t>(1, limit / plan.bytes_per_item));
-    const size_t slot_bytes = align_up((size_t)Gc * clip_bytes);
-    const size_t periods_bytes = align_up((size_t)n_clips * sizeof(int32_t));
-    const size_t need = periods_bytes + 4 * slot_bytes + (size_t)Gw * plan.bytes_per_item;
-    if ((rc = ensure_arena(h, need))) return rc;
-    int32_t* per = reinterpret_cast<int32_t*>(h->arena);
-    float* in_slot[2] = {reinterpret_cast<float*>(h->arena + periods_bytes),
-                         reinterpret_cast<float*>(h->arena + periods_bytes + slot_bytes)};
-    float* out_slot[2] = {reinterpret_cast<float*>(h->arena + periods_bytes + 2 * slot_bytes),
-                          reinterpret_cast<float*>(h->arena + periods_bytes + 3 * slot_bytes)};
-    unsigned char* ws = h->arena + periods_bytes + 4 * slot_bytes;
-    // the caller's stream must see the arena idle before the copy streams touch it
-    CU(cudaStreamSynchronize(h->stream));
-    int n_chunks = 0;
-    for (int first = 0; first < n_clips; first += Gc, ++n_chunks) {
-        const int s = n_chunks & 1;
-        const int g = std::min(Gc, n_clips - first);
-        if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_compute[s], 0));  // slot's input consumed
-        CU(cudaMemcpyAsync(in_slot[s], audio + (size_t)first * clip_elems, (size_t)g * clip_bytes,
-                           cudaMemcpyHostToDevice, h->h2d_stream));
-        CU(cudaEventRecord(h->ev_h2d[s], h->h2d_stream));
-        CU(cudaStreamWaitEvent(h->stream, h->ev_h2d[s], 0));
-        if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_d2h[s], 0));  // slot's output drained
-        rc = original_dev_chunked(h, in_slot[s], g, n_channels, n_samples, p, out_slot[s], per + first, ws,
-                                  (size_t)Gw * plan.bytes_per_item, plan);
-        if (rc) return rc;
-        CU(cudaEventRecord(h->ev_compute[s], h->stream));
-        CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute[s], 0));
-        CU(cudaMemcpyAsync(background + (size_t)first * clip_elems, out_slot[s], (size_t)g * clip_bytes,
-                           cudaMemcpyDeviceToHost, h->d2h_stream));
-        CU(cudaEventRecord(h->ev_d2h[s], h->d2h_stream));
-    }
-    if (periods_host)
-        CU(cudaMemcpyAsync(periods_host, per, (size_t)n_clips * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaStreamSynchronize(h->d2h_stream));
-    return REPET_OK;
-}
-
-int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels,
-                       const repet_params* p, double* background, int32_t* period_host) {
-    int rc = check_common(h, p, n_channels);
-    if (rc) return rc;
-    if (!audio || !background || n_samples < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
-    CU(cudaSetDevice(h->device));
-    OriginalPlan plan;
-    if ((rc = plan_original(h, p, n_channels, n_samples, 1, &plan))) return rc;
-    const size_t n = (size_t)n_samples * n_channels;
-    const size_t f64_bytes = align_up(n * sizeof(double));
-    const size_t f32_bytes = align_up(n * sizeof(float));
-    const size_t need = 256 + f64_bytes + 2 * f32_bytes + plan.bytes_per_item;
-    if ((rc = ensure_arena(h, need))) return rc;
-    Bump bump(h->arena);
-    int32_t* per = bump.take<int32_t>(1);
-    double* d64 = bump.take<double>(n);
-    float* in32 = bump.take<float>(n);
-    float* out32 = bump.take<float>(n);
-    unsigned char* ws = h->arena + bump.off;
-    cudaStream_t st = h->stream;
-    CU(cudaMemcpyAsync(d64, audio, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    {
-        Timed timed(h, REPET_K_CONVERT);
-        launch_f64_interleaved_to_planar(st, d64, n_samples, n_channels, in32);
-    }
-    rc = original_dev_chunked(h, in32, 1, n_channels, n_samples, p, out32, per, ws, plan.bytes_per_item, plan);
-    if (rc) return rc;
-    {
-        Timed timed(h, REPET_K_CONVERT);
-        launch_planar_to_f64_interleaved(st, out32, n_samples, n_channels, d64);
-    }
-    CU(cudaMemcpyAsync(background, d64, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (period_host) CU(cudaMemcpyAsync(period_host, per, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return REPET_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
 int repet_stft(repet_handle* h, const float* signal, int n_channels, int64_t n_samples, float* spectrum, float* power,
@@ -614,6 +315,16 @@ int repet_period(repet_handle* h, const float* spectrogram, int n_frames, int n_
     return beat_common(h, spectrogram, n_frames, n_rows, period_lo, lag_hi, nullptr, period);
 }
 
+// magnitudes [n_frames][1025] as purely real spectra; bin 0 packs (DC, Nyquist)
+static void pack_magnitudes(const float* magnitude, int T, std::vector<float2>& host) {
+    host.resize((size_t)T * XPITCH);
+    for (int j = 0; j < T; ++j) {
+        const float* row = magnitude + (size_t)j * NBIN;
+        host[(size_t)j * XPITCH] = make_float2(row[0], row[XPITCH]);
+        for (int k = 1; k < XPITCH; ++k) host[(size_t)j * XPITCH + k] = make_float2(row[k], 0.f);
+    }
+}
+
 int repet_mask(repet_handle* h, const float* magnitude, int n_frames, int period, float* mask) {
     if (!h) return REPET_E_INVALID_ARG;
     if (!magnitude || !mask || n_frames < 1 || period < 1) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
@@ -629,13 +340,8 @@ int repet_mask(repet_handle* h, const float* magnitude, int n_frames, int period
     float* model = bump.take<float>((size_t)period * PPITCH);
     float* M = bump.take<float>((size_t)T * PPITCH);
     int32_t* per = bump.take<int32_t>(1);
-    // magnitudes as purely real spectra; bin 0 packs (DC, Nyquist)
-    std::vector<float2> host(x_elems);
-    for (int j = 0; j < T; ++j) {
-        const float* row = magnitude + (size_t)j * NBIN;
-        host[(size_t)j * XPITCH] = make_float2(row[0], row[XPITCH]);
-        for (int k = 1; k < XPITCH; ++k) host[(size_t)j * XPITCH + k] = make_float2(row[k], 0.f);
-    }
+    std::vector<float2> host;
+    pack_magnitudes(magnitude, T, host);
     cudaStream_t st = h->stream;
     CU(cudaMemcpyAsync(X, host.data(), x_elems * sizeof(float2), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(per, &period, sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -644,6 +350,97 @@ int repet_mask(repet_handle* h, const float* magnitude, int n_frames, int period
     h->launches += 2;
     CU(cudaMemcpy2DAsync(mask, NBIN * sizeof(float), M, PPITCH * sizeof(float), NBIN * sizeof(float), T,
                          cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_adaptivemask(repet_handle* h, const float* magnitude, int n_frames, const int32_t* periods, int filter_order,
+                       float* mask) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!magnitude || !mask || !periods || n_frames < 1 || filter_order < 1)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    CU(cudaSetDevice(h->device));
+    const int T = n_frames;
+    const size_t x_elems = (size_t)T * XPITCH;
+    const size_t need = align_up(x_elems * sizeof(float2)) + 2 * align_up((size_t)T * PPITCH * sizeof(float)) +
+                        align_up((size_t)T * sizeof(int32_t)) + 512;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    float2* X = bump.take<float2>(x_elems);
+    float* model = bump.take<float>((size_t)T * PPITCH);
+    float* M = bump.take<float>((size_t)T * PPITCH);
+    int32_t* per = bump.take<int32_t>(T);
+    std::vector<float2> host;
+    pack_magnitudes(magnitude, T, host);
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(X, host.data(), x_elems * sizeof(float2), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(per, periods, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    launch_adaptive_model(st, X, 1, T, 1, per, filter_order, model);
+    launch_mask_only(st, X, 1, T, 1, nullptr, T, model, M);
+    h->launches += 2;
+    CU(cudaMemcpy2DAsync(mask, NBIN * sizeof(float), M, PPITCH * sizeof(float), NBIN * sizeof(float), T,
+                         cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_beatspectrogram(repet_handle* h, const float* spectrogram, int n_frames, int n_rows, int segment_length,
+                          int segment_step, double* beat, int32_t* n_segments_out) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!spectrogram || !beat || n_frames < 1 || n_rows < 1 || n_rows > NBIN || segment_length < 1 || segment_step < 1)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size (n_rows <= 1025)");
+    if (2 * segment_length - 1 > BEAT_L)
+        return fail(h, REPET_E_UNSUPPORTED, "segment_length exceeds the 2048-point beat transform");
+    CU(cudaSetDevice(h->device));
+    const int n_seg = (n_frames + segment_step - 1) / segment_step;
+    if (n_segments_out) *n_segments_out = n_seg;
+    const int n_parts = 9, f_per_part = 120;
+    const size_t need = align_up((size_t)n_frames * PPITCH * sizeof(float)) +
+                        align_up((size_t)n_seg * n_parts * BEAT_L * sizeof(float)) +
+                        align_up((size_t)n_seg * segment_length * sizeof(double)) + 512;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    float* P = bump.take<float>((size_t)n_frames * PPITCH);
+    float* psd = bump.take<float>((size_t)n_seg * n_parts * BEAT_L);
+    double* b = bump.take<double>((size_t)n_seg * segment_length);
+    cudaStream_t st = h->stream;
+    CU(cudaMemsetAsync(P, 0, (size_t)n_frames * PPITCH * sizeof(float), st));
+    CU(cudaMemcpy2DAsync(P, PPITCH * sizeof(float), spectrogram, n_rows * sizeof(float), n_rows * sizeof(float), n_frames,
+                         cudaMemcpyHostToDevice, st));
+    const int left = segment_length / 2;  // ceil((L-1)/2), repet.py:1182
+    launch_beat(st, P, 1, n_frames, -left, segment_length, segment_step, n_seg, tables(h), psd, n_parts, f_per_part);
+    launch_periods(st, psd, n_seg, n_parts, segment_length, (double)n_rows, 0, 0, 0, segment_length, b, segment_length,
+                   nullptr, nullptr);
+    h->launches += 2;
+    CU(cudaMemcpyAsync(beat, b, (size_t)n_seg * segment_length * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_periods(repet_handle* h, const double* beat, int n_lags, int n_columns, int period_lo, int period_hi,
+                  int32_t* periods) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!beat || !periods || n_lags < 1 || n_columns < 1) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    const int lag_hi = std::min(period_hi, n_lags / 3);  // repet.py:1265-1267
+    if (period_lo < 0 || lag_hi <= period_lo)
+        return fail(h, REPET_E_TOO_SHORT, "attempt to get argmax of an empty sequence");
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)n_lags * n_columns;
+    int rc = ensure_arena(h, align_up(n * sizeof(double)) + align_up((size_t)n_columns * sizeof(int32_t)));
+    if (rc) return rc;
+    Bump bump(h->arena);
+    double* b = bump.take<double>(n);
+    int32_t* per = bump.take<int32_t>(n_columns);
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(b, beat, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_argmax_columns(st, b, n_lags, n_columns, period_lo, lag_hi, per);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(periods, per, (size_t)n_columns * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     return REPET_OK;

@@ -1,0 +1,487 @@
+// Batch drivers behind the C ABI: repet.original / extended / adaptive (repet.py:67-568) over
+// device-resident clips, their host-buffer variants (chunked, copy/compute overlapped) and the
+// reference's float64 (samples, channels) calling convention.
+#include "repet_internal.h"
+
+#include <cmath>
+#include <functional>
+
+using namespace repet;
+
+namespace {
+
+enum Kind { KIND_ORIGINAL = 0, KIND_EXTENDED = 1, KIND_ADAPTIVE = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// the period pipeline shared by `original` and the segments of `extended`:
+// STFT -> beat spectrum -> period -> median model -> mask + ISTFT
+// ---------------------------------------------------------------------------------------------
+struct PeriodShape {
+    int T = 0, lag_hi = 0, pmax = 0, n_parts = 0, f_per_part = 0;
+    size_t bytes_per_item = 0;
+};
+
+void pick_beat_parts(repet_handle* h, int chunk_hint, int floor_parts, int* n_parts, int* f_per_part) {
+    // measured on B200 (profiles/r1_sweep2.txt): ~64 partitions of the 1025 rows per clip is the sweet spot
+    int want = std::max(floor_parts, std::min(129, (h->sm_count * 6 + chunk_hint - 1) / std::max(1, chunk_hint)));
+    if (g_tuning.beat_parts > 0) want = std::min(129, g_tuning.beat_parts);
+    *f_per_part = ((NBIN + want - 1) / want + 7) / 8 * 8;
+    *n_parts = (NBIN + *f_per_part - 1) / *f_per_part;
+}
+
+int period_shape(repet_handle* h, const repet_params* p, int nch, int64_t n_samples, int chunk_hint, PeriodShape* s) {
+    const int T = frames_of(n_samples);
+    const int lag_hi = std::min(p->period_hi, T / 3);  // repet.py:1265-1267 (quirk Q2)
+    if (p->period_lo < 0 || lag_hi <= p->period_lo)
+        return fail(h, REPET_E_TOO_SHORT,
+                    "attempt to get argmax of an empty sequence (signal too short for the period range)");
+    if (T + lag_hi - 1 > BEAT_L)
+        return fail(h, REPET_E_UNSUPPORTED, "clip longer than the single-block beat transform (T + max lag > 2048 frames)");
+    s->T = T;
+    s->lag_hi = lag_hi;
+    s->pmax = lag_hi;  // period = lag + 1 <= lag_hi
+    pick_beat_parts(h, chunk_hint, 64, &s->n_parts, &s->f_per_part);
+    size_t b = 0;
+    b += align_up((size_t)T * nch * XPITCH * sizeof(float2));
+    b += align_up((size_t)T * PPITCH * sizeof(float));
+    b += align_up((size_t)s->n_parts * BEAT_L * sizeof(float));
+    b += align_up((size_t)nch * s->pmax * PPITCH * sizeof(float));
+    b += 512;
+    s->bytes_per_item = b;
+    return REPET_OK;
+}
+
+int pick_frames_per_cta(repet_handle* h, long long total_frames) {
+    if (g_tuning.frames_per_cta > 0) return g_tuning.frames_per_cta;
+    long long k = total_frames / ((long long)h->sm_count * 8);
+    return (int)std::max(4LL, std::min(16LL, k));
+}
+
+// gin / gout describe ALL items; the pipeline walks them in workspace-sized chunks.
+int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, Geom gout, int nch,
+                    const repet_params* p, const PeriodShape& s, int32_t* periods_dev, unsigned char* ws,
+                    size_t ws_bytes) {
+    const int n_items = gin.n_items;
+    const int G = (int)std::min<size_t>(std::min<size_t>((size_t)n_items, MAX_ITEMS_PER_LAUNCH),
+                                        std::max<size_t>(1, ws_bytes / s.bytes_per_item));
+    const float scale = (float)(1.0 / ((double)WIN_N * p->cola_gain));
+    cudaStream_t st = h->stream;
+    for (int first = 0; first < n_items; first += G) {
+        const int g_items = std::min(G, n_items - first);
+        Bump bump(ws);
+        float2* X = bump.take<float2>((size_t)g_items * s.T * nch * XPITCH);
+        float* P = bump.take<float>((size_t)g_items * s.T * PPITCH);
+        float* psd = bump.take<float>((size_t)g_items * s.n_parts * BEAT_L);
+        float* model = bump.take<float>((size_t)g_items * nch * s.pmax * PPITCH);
+        gin.n_items = gout.n_items = g_items;
+        gin.item0 = gout.item0 = first;
+        const int K = pick_frames_per_cta(h, (long long)g_items * s.T);
+        {
+            Timed timed(h, REPET_K_STFT);
+            launch_stft(st, audio, gin, nch, h->window, tables(h), X, P, P_POWER, K);
+        }
+        {
+            Timed timed(h, REPET_K_BEAT);
+            launch_beat(st, P, g_items, s.T, 0, s.T, 0, 1, tables(h), psd, s.n_parts, s.f_per_part);
+        }
+        {
+            Timed timed(h, REPET_K_PERIODS);
+            launch_periods(st, psd, g_items, s.n_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr, 0,
+                           periods_dev + first, nullptr);
+        }
+        {
+            Timed timed(h, REPET_K_MODEL);
+            launch_model(st, X, g_items, s.T, nch, periods_dev + first, s.pmax, model);
+        }
+        {
+            Timed timed(h, REPET_K_MASK_ISTFT);
+            launch_mask_istft(st, X, gout, nch, periods_dev + first, s.pmax, model, p->cutoff_bins, scale, tables(h), out, K);
+        }
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+Geom clip_geom(int n_clips, int nch, int64_t n_samples, int T) {
+    Geom g;
+    g.n_items = n_clips;
+    g.seg_per_clip = 1;
+    g.clip_stride = (long long)nch * n_samples;
+    g.seg_stride = 0;
+    g.chan_stride = n_samples;
+    g.first_offset = 0;
+    g.S = (int)n_samples;
+    g.T = T;
+    g.item0 = 0;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-kind plans: workspace per clip, integer outputs per clip, and the device-resident runner
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+    int kind = 0, nch = 0;
+    int64_t S = 0;
+    int T = 0;
+    repet_params p;
+    PeriodShape whole;  // original; extended when the signal is a single segment
+    // extended (repet.py:266-281)
+    int n_seg = 1, seg_len = 0, last_len = 0, step = 0;
+    PeriodShape seg_main, seg_last;
+    // adaptive (repet.py:519-520, 1174-1188)
+    int seg_frames = 0, step_frames = 0, n_beat_seg = 0, left_pad = 0, lag_hi = 0, beat_parts = 0, beat_f_per_part = 0;
+    int ints_per_clip = 1;
+    size_t bytes_per_clip = 0;
+};
+
+int make_plan(repet_handle* h, int kind, const repet_params* p, int nch, int64_t S, int chunk_hint, Plan* plan) {
+    plan->kind = kind;
+    plan->nch = nch;
+    plan->S = S;
+    plan->T = frames_of(S);
+    plan->p = *p;
+    int rc;
+    if (S > 2147483647LL - 4096) return fail(h, REPET_E_UNSUPPORTED, "more than 2^31 samples per clip");
+    if (kind == KIND_ORIGINAL) {
+        if ((rc = period_shape(h, p, nch, S, chunk_hint, &plan->whole))) return rc;
+        plan->ints_per_clip = 1;
+        plan->bytes_per_clip = plan->whole.bytes_per_item;
+        return REPET_OK;
+    }
+    if (kind == KIND_EXTENDED) {
+        const int64_t seg_len = p->segment_length, step = p->segment_step;
+        if (seg_len <= 0 || step <= 0 || seg_len <= step)
+            return fail(h, REPET_E_INVALID_ARG, "segment_length must exceed segment_step (both positive)");
+        if (S < seg_len + step) {  // repet.py:271-274: a single segment, i.e. the original REPET
+            plan->n_seg = 1;
+            if ((rc = period_shape(h, p, nch, S, chunk_hint, &plan->whole))) return rc;
+            plan->ints_per_clip = 1;
+            plan->bytes_per_clip = plan->whole.bytes_per_item;
+            return REPET_OK;
+        }
+        plan->n_seg = 1 + (int)((S - seg_len) / step);  // repet.py:279-281
+        plan->seg_len = (int)seg_len;
+        plan->step = (int)step;
+        plan->last_len = (int)(S - (int64_t)(plan->n_seg - 1) * step);  // repet.py:320-322
+        const int main_hint = chunk_hint * std::max(1, plan->n_seg - 1);
+        if ((rc = period_shape(h, p, nch, seg_len, main_hint, &plan->seg_main))) return rc;
+        if ((rc = period_shape(h, p, nch, plan->last_len, chunk_hint, &plan->seg_last))) return rc;
+        plan->ints_per_clip = plan->n_seg;
+        size_t b = 0;
+        b += align_up((size_t)(plan->n_seg - 1) * nch * seg_len * sizeof(float));
+        b += align_up((size_t)nch * plan->last_len * sizeof(float));
+        b += (size_t)(plan->n_seg - 1) * plan->seg_main.bytes_per_item + plan->seg_last.bytes_per_item;
+        b += 1024;
+        plan->bytes_per_clip = b;
+        return REPET_OK;
+    }
+    if (kind == KIND_ADAPTIVE) {
+        const int L = p->segment_length, step = p->segment_step;
+        if (L <= 0 || step <= 0) return fail(h, REPET_E_INVALID_ARG, "segment length and step must be positive");
+        if (p->filter_order < 1) return fail(h, REPET_E_INVALID_ARG, "filter_order must be at least 1");
+        const int lag_hi = std::min(p->period_hi, L / 3);  // n_lags of the beat spectrogram = segment length
+        if (p->period_lo < 0 || lag_hi <= p->period_lo)
+            return fail(h, REPET_E_TOO_SHORT, "attempt to get argmax of an empty sequence (segment too short for the period range)");
+        if (L + lag_hi - 1 > BEAT_L)
+            return fail(h, REPET_E_UNSUPPORTED, "segment longer than the single-block beat transform");
+        plan->seg_frames = L;
+        plan->step_frames = step;
+        plan->lag_hi = lag_hi;
+        plan->left_pad = (L - 1 + 1) / 2;  // ceil((L-1)/2), repet.py:1182
+        plan->n_beat_seg = (plan->T + step - 1) / step;
+        pick_beat_parts(h, chunk_hint * plan->n_beat_seg, 4, &plan->beat_parts, &plan->beat_f_per_part);
+        plan->ints_per_clip = plan->T;
+        size_t b = 0;
+        b += align_up((size_t)plan->T * nch * XPITCH * sizeof(float2));
+        b += align_up((size_t)plan->T * PPITCH * sizeof(float));
+        b += align_up((size_t)plan->n_beat_seg * plan->beat_parts * BEAT_L * sizeof(float));
+        b += align_up((size_t)plan->n_beat_seg * sizeof(int32_t));
+        b += align_up((size_t)nch * plan->T * PPITCH * sizeof(float));
+        b += 1024;
+        plan->bytes_per_clip = b;
+        return REPET_OK;
+    }
+    return fail(h, REPET_E_INVALID_ARG, "unknown driver kind");
+}
+
+int run_extended(repet_handle* h, const Plan& plan, const float* audio, int n_clips, float* out, int32_t* ints,
+                 unsigned char* ws, size_t ws_bytes) {
+    const int nch = plan.nch;
+    const int n_main = plan.n_seg - 1;
+    const int G = (int)std::min<size_t>((size_t)n_clips, std::max<size_t>(1, ws_bytes / plan.bytes_per_clip));
+    cudaStream_t st = h->stream;
+    for (int clip0 = 0; clip0 < n_clips; clip0 += G) {
+        const int g = std::min(G, n_clips - clip0);
+        Bump bump(ws);
+        float* seg_main = bump.take<float>((size_t)g * n_main * nch * plan.seg_len);
+        float* seg_last = bump.take<float>((size_t)g * nch * plan.last_len);
+        int32_t* per_main = bump.take<int32_t>((size_t)g * n_main);
+        int32_t* per_last = bump.take<int32_t>((size_t)g);
+        unsigned char* pws = ws + bump.off;
+        const size_t pws_bytes = ws_bytes - bump.off;
+        const float* a = audio + (size_t)clip0 * nch * plan.S;
+        // equally long segments j < n_seg-1 (repet.py:318-319)
+        Geom gin = clip_geom(g * n_main, nch, plan.S, plan.seg_main.T);
+        gin.seg_per_clip = n_main;
+        gin.seg_stride = plan.step;
+        gin.S = plan.seg_len;
+        Geom gout = clip_geom(g * n_main, nch, plan.seg_len, plan.seg_main.T);
+        int rc = period_pipeline(h, a, gin, seg_main, gout, nch, &plan.p, plan.seg_main, per_main, pws, pws_bytes);
+        if (rc) return rc;
+        // the last segment takes the remainder (repet.py:320-322)
+        gin = clip_geom(g, nch, plan.S, plan.seg_last.T);
+        gin.first_offset = (long long)n_main * plan.step;
+        gin.S = plan.last_len;
+        gout = clip_geom(g, nch, plan.last_len, plan.seg_last.T);
+        rc = period_pipeline(h, a, gin, seg_last, gout, nch, &plan.p, plan.seg_last, per_last, pws, pws_bytes);
+        if (rc) return rc;
+        {
+            Timed timed(h, REPET_K_XFADE);
+            launch_xfade(st, seg_main, seg_last, g, plan.n_seg, plan.seg_len, plan.last_len, plan.step, nch, plan.S,
+                         out + (size_t)clip0 * nch * plan.S);
+        }
+        int32_t* dst = ints + (size_t)clip0 * plan.n_seg;
+        CU(cudaMemcpy2DAsync(dst, plan.n_seg * sizeof(int32_t), per_main, n_main * sizeof(int32_t),
+                             n_main * sizeof(int32_t), g, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpy2DAsync(dst + n_main, plan.n_seg * sizeof(int32_t), per_last, sizeof(int32_t), sizeof(int32_t), g,
+                             cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_clips, float* out, int32_t* ints,
+                 unsigned char* ws, size_t ws_bytes) {
+    const int nch = plan.nch, T = plan.T;
+    const int G = (int)std::min<size_t>(std::min<size_t>((size_t)n_clips, MAX_ITEMS_PER_LAUNCH / 2),
+                                        std::max<size_t>(1, ws_bytes / plan.bytes_per_clip));
+    const float scale = (float)(1.0 / ((double)WIN_N * plan.p.cola_gain));
+    cudaStream_t st = h->stream;
+    for (int clip0 = 0; clip0 < n_clips; clip0 += G) {
+        const int g = std::min(G, n_clips - clip0);
+        Bump bump(ws);
+        float2* X = bump.take<float2>((size_t)g * T * nch * XPITCH);
+        float* P = bump.take<float>((size_t)g * T * PPITCH);
+        float* psd = bump.take<float>((size_t)g * plan.n_beat_seg * plan.beat_parts * BEAT_L);
+        int32_t* seg_period = bump.take<int32_t>((size_t)g * plan.n_beat_seg);
+        float* model = bump.take<float>((size_t)g * nch * T * PPITCH);
+        int32_t* frame_period = ints + (size_t)clip0 * T;
+        Geom geom = clip_geom(g, nch, plan.S, T);
+        geom.first_offset = (long long)clip0 * geom.clip_stride;
+        const int K = pick_frames_per_cta(h, (long long)g * T);
+        {
+            Timed timed(h, REPET_K_STFT);
+            launch_stft(st, audio, geom, nch, h->window, tables(h), X, P, P_POWER, K);
+        }
+        {
+            // segment i spans frames [i - left_pad, i - left_pad + L) (zero outside), repet.py:1177-1198
+            Timed timed(h, REPET_K_BEAT);
+            launch_beat(st, P, g, T, -plan.left_pad, plan.seg_frames, plan.step_frames, plan.n_beat_seg, tables(h), psd,
+                        plan.beat_parts, plan.beat_f_per_part);
+        }
+        {
+            Timed timed(h, REPET_K_PERIODS);
+            launch_periods(st, psd, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
+                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr);
+        }
+        {
+            Timed timed(h, REPET_K_MODEL);
+            launch_expand_periods(st, seg_period, g, plan.n_beat_seg, T, plan.step_frames, plan.p.period_lo, frame_period);
+            launch_adaptive_model(st, X, g, T, nch, frame_period, plan.p.filter_order, model);
+        }
+        {
+            Timed timed(h, REPET_K_MASK_ISTFT);
+            launch_mask_istft(st, X, geom, nch, nullptr, T, model, plan.p.cutoff_bins, scale, tables(h), out, K);
+        }
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+// device-resident run of `n_clips` clips starting at `audio` / `out` / `ints`
+int run_plan(repet_handle* h, const Plan& plan, const float* audio, int n_clips, float* out, int32_t* ints,
+             unsigned char* ws, size_t ws_bytes) {
+    if (plan.kind == KIND_ORIGINAL || (plan.kind == KIND_EXTENDED && plan.n_seg == 1)) {
+        Geom g = clip_geom(n_clips, plan.nch, plan.S, plan.whole.T);
+        return period_pipeline(h, audio, g, out, g, plan.nch, &plan.p, plan.whole, ints, ws, ws_bytes);
+    }
+    if (plan.kind == KIND_EXTENDED) return run_extended(h, plan, audio, n_clips, out, ints, ws, ws_bytes);
+    return run_adaptive(h, plan, audio, n_clips, out, ints, ws, ws_bytes);
+}
+
+int chunk_clips(repet_handle* h, const Plan& plan, int n_clips) {
+    const size_t limit = default_ws_limit(h);
+    return (int)std::min<size_t>((size_t)n_clips, std::max<size_t>(1, limit / plan.bytes_per_clip));
+}
+
+// ---------------------------------------------------------------------------------------------
+// the three calling conventions
+// ---------------------------------------------------------------------------------------------
+int batch_dev(repet_handle* h, int kind, const float* audio, int n_clips, int nch, int64_t S, const repet_params* p,
+              float* background, int32_t* ints_dev, int32_t* ints_host, int* ints_per_clip_out) {
+    int rc = check_common(h, p, nch);
+    if (rc) return rc;
+    if (!audio || !background || n_clips < 0 || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    CU(cudaSetDevice(h->device));
+    Plan plan;
+    if ((rc = make_plan(h, kind, p, nch, S, std::max(1, std::min(n_clips, 64)), &plan))) return rc;
+    int G = chunk_clips(h, plan, n_clips);
+    if ((rc = make_plan(h, kind, p, nch, S, std::max(1, G), &plan))) return rc;
+    if (ints_per_clip_out) *ints_per_clip_out = plan.ints_per_clip;
+    if (n_clips == 0) return REPET_OK;
+    G = chunk_clips(h, plan, n_clips);
+    const size_t ints_bytes = ints_dev ? 0 : align_up((size_t)n_clips * plan.ints_per_clip * sizeof(int32_t));
+    if ((rc = ensure_arena(h, ints_bytes + (size_t)G * plan.bytes_per_clip))) return rc;
+    int32_t* ints = ints_dev ? ints_dev : reinterpret_cast<int32_t*>(h->arena);
+    rc = run_plan(h, plan, audio, n_clips, background, ints, h->arena + ints_bytes, (size_t)G * plan.bytes_per_clip);
+    if (rc) return rc;
+    if (ints_host) {
+        CU(cudaMemcpyAsync(ints_host, ints, (size_t)n_clips * plan.ints_per_clip * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                           h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return REPET_OK;
+}
+
+int batch_host(repet_handle* h, int kind, const float* audio, int n_clips, int nch, int64_t S, const repet_params* p,
+               float* background, int32_t* ints_host) {
+    int rc = check_common(h, p, nch);
+    if (rc) return rc;
+    if (!audio || !background || n_clips < 0 || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    if (n_clips == 0) return REPET_OK;
+    CU(cudaSetDevice(h->device));
+    const size_t clip_elems = (size_t)nch * (size_t)S;
+    const size_t clip_bytes = clip_elems * sizeof(float);
+    // copy granularity: about 256 MB per slot, two slots in flight in each direction
+    int Gc = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_clips, ((size_t)256 << 20) / std::max<size_t>(1, clip_bytes)));
+    Plan plan;
+    if ((rc = make_plan(h, kind, p, nch, S, Gc, &plan))) return rc;
+    const int Gw = std::min(Gc, chunk_clips(h, plan, Gc));
+    const size_t slot_bytes = align_up((size_t)Gc * clip_bytes);
+    const size_t ints_bytes = align_up((size_t)n_clips * plan.ints_per_clip * sizeof(int32_t));
+    const size_t ws_bytes = (size_t)Gw * plan.bytes_per_clip;
+    if ((rc = ensure_arena(h, ints_bytes + 4 * slot_bytes + ws_bytes))) return rc;
+    int32_t* ints = reinterpret_cast<int32_t*>(h->arena);
+    float* in_slot[2] = {reinterpret_cast<float*>(h->arena + ints_bytes),
+                         reinterpret_cast<float*>(h->arena + ints_bytes + slot_bytes)};
+    float* out_slot[2] = {reinterpret_cast<float*>(h->arena + ints_bytes + 2 * slot_bytes),
+                          reinterpret_cast<float*>(h->arena + ints_bytes + 3 * slot_bytes)};
+    unsigned char* ws = h->arena + ints_bytes + 4 * slot_bytes;
+    CU(cudaStreamSynchronize(h->stream));  // the arena must be idle before the copy streams touch it
+    int n_chunks = 0;
+    for (int first = 0; first < n_clips; first += Gc, ++n_chunks) {
+        const int s = n_chunks & 1;
+        const int g = std::min(Gc, n_clips - first);
+        if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_compute[s], 0));  // slot's input consumed
+        CU(cudaMemcpyAsync(in_slot[s], audio + (size_t)first * clip_elems, (size_t)g * clip_bytes, cudaMemcpyHostToDevice,
+                           h->h2d_stream));
+        CU(cudaEventRecord(h->ev_h2d[s], h->h2d_stream));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_h2d[s], 0));
+        if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_d2h[s], 0));  // slot's output drained
+        rc = run_plan(h, plan, in_slot[s], g, out_slot[s], ints + (size_t)first * plan.ints_per_clip, ws, ws_bytes);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_compute[s], h->stream));
+        CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute[s], 0));
+        CU(cudaMemcpyAsync(background + (size_t)first * clip_elems, out_slot[s], (size_t)g * clip_bytes,
+                           cudaMemcpyDeviceToHost, h->d2h_stream));
+        CU(cudaEventRecord(h->ev_d2h[s], h->d2h_stream));
+    }
+    if (ints_host)
+        CU(cudaMemcpyAsync(ints_host, ints, (size_t)n_clips * plan.ints_per_clip * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                           h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->d2h_stream));
+    return REPET_OK;
+}
+
+// float64 (samples, channels) in and out -- the reference's own convention (repet.py:73-77)
+int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nch, const repet_params* p,
+               double* background, int32_t* ints_host, int ints_capacity) {
+    int rc = check_common(h, p, nch);
+    if (rc) return rc;
+    if (!audio || !background || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    CU(cudaSetDevice(h->device));
+    Plan plan;
+    if ((rc = make_plan(h, kind, p, nch, S, 1, &plan))) return rc;
+    if (ints_host && ints_capacity < plan.ints_per_clip)
+        return fail(h, REPET_E_INVALID_ARG, "integer output buffer too small");
+    const size_t n = (size_t)S * nch;
+    const size_t need = align_up((size_t)plan.ints_per_clip * sizeof(int32_t)) + align_up(n * sizeof(double)) +
+                        2 * align_up(n * sizeof(float)) + plan.bytes_per_clip;
+    if ((rc = ensure_arena(h, need))) return rc;
+    Bump bump(h->arena);
+    int32_t* ints = bump.take<int32_t>(plan.ints_per_clip);
+    double* d64 = bump.take<double>(n);
+    float* in32 = bump.take<float>(n);
+    float* out32 = bump.take<float>(n);
+    unsigned char* ws = h->arena + bump.off;
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(d64, audio, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        Timed timed(h, REPET_K_CONVERT);
+        launch_f64_interleaved_to_planar(st, d64, S, nch, in32);
+    }
+    if ((rc = run_plan(h, plan, in32, 1, out32, ints, ws, plan.bytes_per_clip))) return rc;
+    {
+        Timed timed(h, REPET_K_CONVERT);
+        launch_planar_to_f64_interleaved(st, out32, S, nch, d64);
+    }
+    CU(cudaMemcpyAsync(background, d64, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ints_host)
+        CU(cudaMemcpyAsync(ints_host, ints, (size_t)plan.ints_per_clip * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return REPET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- repet.original (repet.py:67-202) ------------------------------------------------------
+int repet_original_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
+    return batch_dev(h, KIND_ORIGINAL, audio, n_clips, n_channels, n_samples, p, background, periods_dev, periods_host, nullptr);
+}
+int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                         const repet_params* p, float* background, int32_t* periods_host) {
+    return batch_host(h, KIND_ORIGINAL, audio, n_clips, n_channels, n_samples, p, background, periods_host);
+}
+int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                       double* background, int32_t* period_host) {
+    return single_f64(h, KIND_ORIGINAL, audio, n_samples, n_channels, p, background, period_host, 1);
+}
+
+// ---- repet.extended (repet.py:205-419) -----------------------------------------------------
+int repet_extended_segments(const repet_params* p, int64_t n_samples) {
+    if (!p || p->segment_length <= 0 || p->segment_step <= 0) return 0;
+    if (n_samples < (int64_t)p->segment_length + p->segment_step) return 1;
+    return 1 + (int)((n_samples - p->segment_length) / p->segment_step);
+}
+int repet_extended_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
+    return batch_dev(h, KIND_EXTENDED, audio, n_clips, n_channels, n_samples, p, background, periods_dev, periods_host, nullptr);
+}
+int repet_extended_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                         const repet_params* p, float* background, int32_t* periods_host) {
+    return batch_host(h, KIND_EXTENDED, audio, n_clips, n_channels, n_samples, p, background, periods_host);
+}
+int repet_extended_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                       double* background, int32_t* periods_host, int periods_capacity) {
+    return single_f64(h, KIND_EXTENDED, audio, n_samples, n_channels, p, background, periods_host, periods_capacity);
+}
+
+// ---- repet.adaptive (repet.py:422-568) -----------------------------------------------------
+int repet_adaptive_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
+    return batch_dev(h, KIND_ADAPTIVE, audio, n_clips, n_channels, n_samples, p, background, periods_dev, periods_host, nullptr);
+}
+int repet_adaptive_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                         const repet_params* p, float* background, int32_t* periods_host) {
+    return batch_host(h, KIND_ADAPTIVE, audio, n_clips, n_channels, n_samples, p, background, periods_host);
+}
+int repet_adaptive_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                       double* background, int32_t* periods_host, int periods_capacity) {
+    return single_f64(h, KIND_ADAPTIVE, audio, n_samples, n_channels, p, background, periods_host, periods_capacity);
+}
+
+}  // extern "C"

@@ -39,7 +39,8 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
     float wv[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) wv[n1] = __ldg(&window[n1 * 128 + t]);
-    const int clip = item / g.seg_per_clip, sg = item - clip * g.seg_per_clip;
+    const int gitem = g.item0 + item;
+    const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
     const float* __restrict__ a0 = audio + g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
     const float* __restrict__ a1 = a0 + g.chan_stride;
     float cl[8], cr[8];
@@ -493,11 +494,12 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     s_tw2[t] = tb.tw2[t];
     Twiddle1 tw;
     tw.load(tb.tw1, t);
-    const int clip = item / g.seg_per_clip, sg = item - clip * g.seg_per_clip;
+    const int gitem = g.item0 + item;
+    const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
     float* __restrict__ o0 = out + g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
     float* __restrict__ o1 = o0 + g.chan_stride;
     int p = 1;
-    if (MASKED) p = period[item];
+    if (MASKED) p = period ? period[item] : pmax;  // no period array: one model row per frame (adaptive, sim)
     float carry_l[8], carry_r[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) carry_l[i] = carry_r[i] = 0.f;
@@ -622,7 +624,7 @@ k_mask_only(const float2* __restrict__ X, int T, int nch, const int* __restrict_
     const int j = blockIdx.y;
     const int k = blockIdx.x * 128 + threadIdx.x;
     if (k > XPITCH) return;
-    const int p = period[item];
+    const int p = period ? period[item] : pmax;
     const float2* __restrict__ row = X + ((size_t)item * T + j) * (size_t)(nch * XPITCH) + (size_t)c * XPITCH;
     const float m = model[(((size_t)item * nch + c) * pmax + (j % p)) * PPITCH + k];
     mask_out[(((size_t)item * nch + c) * T + j) * PPITCH + k] = soft_mask(m, row_mag2(row, k));
@@ -632,6 +634,165 @@ void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int 
                       const float* model, float* mask_out) {
     dim3 grid(9, T, n_items * nch);
     k_mask_only<<<grid, 128, 0, st>>>(X, T, nch, period, pmax, model, mask_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_expand_periods  --  per-frame periods of the adaptive REPET        repet.py:1194-1204, 1274-1289
+// Segment i = 0, step, 2 step, ... of the beat spectrogram is replicated over columns
+// i .. i+step-2; column i+step-1 stays all-zero in the reference, so its argmax is 0 and its
+// period is lo + 1 (quirk Q3).
+// ------------------------------------------------------------------------------------------
+__global__ void k_expand_periods(const int* __restrict__ seg_period, int n_seg, int T, int step, int lag_lo,
+                                 int* __restrict__ frame_period) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int item = blockIdx.y;
+    if (j >= T) return;
+    const int sI = j / step;
+    const bool zero_column = step > 1 && (j - sI * step) == step - 1;
+    frame_period[(size_t)item * T + j] = zero_column ? lag_lo + 1 : seg_period[(size_t)item * n_seg + sI];
+}
+
+void launch_expand_periods(cudaStream_t st, const int* seg_period, int n_items, int n_seg, int T, int step, int lag_lo,
+                           int* frame_period) {
+    dim3 grid((T + 255) / 256, n_items);
+    k_expand_periods<<<grid, 256, 0, st>>>(seg_period, n_seg, T, step, lag_lo, frame_period);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_adaptive_model  --  the per-frame median of _adaptivemask            repet.py:1474-1498
+// model[f, i] = median{ V[f, i + c p_i] : c in {1..order} - ceil(order/2), 0 <= i + c p_i < T }.
+// The in-range offsets are contiguous in c, so every frame is a strided gather (start frame,
+// stride p_i, count n) and reuses the pair-load median of k_model.  One model row per frame.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_adaptive_model(const float2* __restrict__ X, int T, int nch, const int* __restrict__ frame_period, int order,
+                 float* __restrict__ model, int n_groups) {
+    const int item = blockIdx.y / nch, c = blockIdx.y - item * nch;
+    const int t = threadIdx.x;
+    const int half = (order + 1) / 2;  // ceil(order / 2)
+    const size_t row = (size_t)nch * XPITCH;
+    const float2* __restrict__ chan = X + (size_t)item * T * row + (size_t)c * XPITCH;
+    float* __restrict__ mrow = model + ((size_t)item * nch + c) * (size_t)T * PPITCH;
+    const int* __restrict__ fp = frame_period + (size_t)item * T;
+    const bool nyquist_cta = (int)blockIdx.x == n_groups;
+    const int j_begin = nyquist_cta ? t : blockIdx.x * MODEL_QB;
+    const int j_end = nyquist_cta ? T : min(T, j_begin + MODEL_QB);
+    const int j_step = nyquist_cta ? 128 : 1;
+    for (int j = j_begin; j < j_end; j += j_step) {
+        const int p = fp[j];
+        int c_lo = 1 - half, c_hi = order - half;
+        if (p > 0) {
+            c_lo = max(c_lo, -(j / p));
+            c_hi = min(c_hi, (T - 1 - j) / p);
+        } else {
+            c_lo = c_hi = 0;
+        }
+        const int n = c_hi - c_lo + 1;
+        const float2* __restrict__ base = chan + (size_t)(j + c_lo * p) * row;
+        const size_t stride = (size_t)max(p, 0) * row;
+        float* __restrict__ out = mrow + (size_t)j * PPITCH;
+        if (nyquist_cta) {
+            float med;
+            switch (n) {
+#define REPET_CASE(N) case N: med = strided_median<N>(base, stride, XPITCH); break;
+                REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+                REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+                REPET_CASE(15) REPET_CASE(16)
+#undef REPET_CASE
+                default:
+                    med = median_by_rank(n, [&](int s) { return row_mag2(base + (size_t)s * stride, XPITCH); });
+            }
+            out[XPITCH] = med;
+            continue;
+        }
+        switch (n) {
+#define REPET_CASE(N) case N: model_phase<N>(base, stride, out, t); break;
+            REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+            REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+            REPET_CASE(15) REPET_CASE(16)
+#undef REPET_CASE
+            default:
+                for (int k = t; k < XPITCH; k += 128)
+                    out[k] = median_by_rank(n, [&](int s) { return row_mag2(base + (size_t)s * stride, k); });
+        }
+    }
+}
+
+void launch_adaptive_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* frame_period,
+                           int order, float* model) {
+    const int n_groups = (T + MODEL_QB - 1) / MODEL_QB;
+    dim3 grid(n_groups + 1, n_items * nch);
+    k_adaptive_model<<<grid, 128, 0, st>>>(X, T, nch, frame_period, order, model, n_groups);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_xfade  --  the segment cross-fade of REPET extended                       repet.py:388-414
+// Per output sample, the covering segments are visited in order exactly as the reference's
+// in-place loop does: the first contributes as is; a later one scales what is already there by
+// the falling half of triang(2*overlap) and adds itself scaled by the rising half over its
+// first `overlap` samples, and simply adds beyond.
+// ------------------------------------------------------------------------------------------
+__global__ void k_xfade(const float* __restrict__ seg_main, const float* __restrict__ seg_last, int n_seg, int seg_len,
+                        int last_len, int step, int nch, long long S, float* __restrict__ out) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= S) return;
+    const int clip = blockIdx.y / nch, c = blockIdx.y - clip * nch;
+    const int ov = seg_len - step;
+    int sg_lo = u < seg_len ? 0 : (int)((u - seg_len) / step) + 1;
+    sg_lo = min(sg_lo, n_seg - 1);
+    const int sg_hi = (int)min((long long)(n_seg - 1), u / step);
+    const float inv = 1.0f / (float)(2 * ov);
+    float val = 0.f;
+    for (int sg = sg_lo; sg <= sg_hi; ++sg) {
+        const long long k = (long long)sg * step;
+        const long long i = u - k;
+        float x;
+        if (sg < n_seg - 1)
+            x = seg_main[(((size_t)clip * (n_seg - 1) + sg) * nch + c) * (size_t)seg_len + i];
+        else
+            x = seg_last[((size_t)clip * nch + c) * (size_t)last_len + i];
+        if (sg > 0 && i < ov) {
+            const float up = (float)(2 * i + 1) * inv;               // triang(2 ov)[i]
+            const float down = (float)(2 * (ov - 1 - i) + 1) * inv;  // triang(2 ov)[ov + i]
+            val = val * down + x * up;
+        } else {
+            val += x;
+        }
+    }
+    out[((size_t)clip * nch + c) * (size_t)S + u] = val;
+}
+
+void launch_xfade(cudaStream_t st, const float* seg_main, const float* seg_last, int n_clips, int n_seg, int seg_len,
+                  int last_len, int step, int nch, long long S, float* out) {
+    dim3 grid((unsigned)((S + 255) / 256), n_clips * nch);
+    k_xfade<<<grid, 256, 0, st>>>(seg_main, seg_last, n_seg, seg_len, last_len, step, nch, S, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_argmax_columns  --  _periods on a caller-provided beat spectrum / spectrogram
+//                                                                        repet.py:1249-1291
+// beat[n_lags][n_columns] row-major float64; first maximum over lags [lo, hi) + 1 per column.
+// ------------------------------------------------------------------------------------------
+__global__ void k_argmax_columns(const double* __restrict__ beat, int n_columns, int lag_lo, int lag_hi,
+                                 int* __restrict__ period) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n_columns) return;
+    double best = beat[(size_t)lag_lo * n_columns + col];
+    int arg = lag_lo;
+    for (int l = lag_lo + 1; l < lag_hi; ++l) {
+        const double v = beat[(size_t)l * n_columns + col];
+        if (v > best) {
+            best = v;
+            arg = l;
+        }
+    }
+    period[col] = arg + 1;
+}
+
+void launch_argmax_columns(cudaStream_t st, const double* beat, int n_lags, int n_columns, int lag_lo, int lag_hi,
+                           int* period) {
+    (void)n_lags;
+    k_argmax_columns<<<(n_columns + 127) / 128, 128, 0, st>>>(beat, n_columns, lag_lo, lag_hi, period);
 }
 
 // ------------------------------------------------------------------------------------------

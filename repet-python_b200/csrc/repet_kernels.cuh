@@ -25,6 +25,7 @@ struct Geom {
     long long first_offset;  // added to every item start
     int S;                   // samples per item
     int T;                   // STFT frames per item
+    int item0;               // global index of this launch's first item (workspace indices are local)
 };
 
 struct FftTables {
@@ -72,6 +73,19 @@ void launch_istft(cudaStream_t st, const float2* X, Geom g_out, int nch, float s
 // mask only (helper-level): writes M[item][c][T][PPITCH]
 void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
                       const float* model, float* mask_out);
+
+// adaptive: per-frame periods from per-segment periods (quirk Q3), per-frame median model
+void launch_expand_periods(cudaStream_t st, const int* seg_period, int n_items, int n_seg, int T, int step, int lag_lo,
+                           int* frame_period);
+void launch_adaptive_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* frame_period,
+                           int order, float* model);
+// extended: triangular cross-fade of the separated segments
+void launch_xfade(cudaStream_t st, const float* seg_main, const float* seg_last, int n_clips, int n_seg, int seg_len,
+                  int last_len, int step, int nch, long long S, float* out);
+
+// _periods on caller-provided float64 beat spectra
+void launch_argmax_columns(cudaStream_t st, const double* beat, int n_lags, int n_columns, int lag_lo, int lag_hi,
+                           int* period);
 
 // layout converters for the float64 (S, C) NumPy convention of the reference API
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out);

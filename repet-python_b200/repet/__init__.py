@@ -98,6 +98,16 @@ def original_batch(audio_signals, sampling_frequency):
     return _host.original_batch(audio_signals, sampling_frequency, _tunables())
 
 
+def extended_batch(audio_signals, sampling_frequency):
+    """REPET extended over a batch (see original_batch); periods: int32 (number_clips, number_segments)."""
+    return _host.driver_batch("extended", audio_signals, sampling_frequency, _tunables())
+
+
+def adaptive_batch(audio_signals, sampling_frequency):
+    """The adaptive REPET over a batch (see original_batch); periods: int32 (number_clips, number_times)."""
+    return _host.driver_batch("adaptive", audio_signals, sampling_frequency, _tunables())
+
+
 def extended(audio_signal, sampling_frequency):
     """Compute REPET extended (repet.py:205-419)."""
     return _host.extended_f64(audio_signal, sampling_frequency, _tunables())
@@ -211,6 +221,21 @@ def _istft(audio_stft, window_function, step_length):
 def _beatspectrum(audio_spectrogram):
     """Beat spectrum (repet.py:1142-1158): (number_frequencies, number_times) -> (number_times,)."""
     return _host.beatspectrum(audio_spectrogram)
+
+
+def _beatspectrogram(audio_spectrogram, segment_length, segment_step):
+    """Beat spectrogram (repet.py:1161-1206): (number_frequencies, number_times) -> (segment_length, number_times)."""
+    return _host.beatspectrogram(audio_spectrogram, segment_length, segment_step)
+
+
+def _periods(beat_spectrogram, period_range):
+    """Repeating period(s) from a beat spectrum or beat spectrogram (repet.py:1249-1291)."""
+    return _host.periods(beat_spectrogram, period_range)
+
+
+def _adaptivemask(audio_spectrogram, repeating_periods, filter_order):
+    """Repeating mask for the adaptive REPET (repet.py:1461-1508)."""
+    return _host.adaptivemask(audio_spectrogram, repeating_periods, filter_order)
 
 
 def _mask(audio_spectrogram, repeating_period):

@@ -73,6 +73,16 @@ SIGNATURES = {
     "repet_original_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_original_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
     "repet_original_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp]),
+    "repet_extended_segments": (_c_int, [_pp, _c_i64]),
+    "repet_extended_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
+    "repet_extended_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_extended_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
+    "repet_adaptive_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
+    "repet_adaptive_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_adaptive_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
+    "repet_adaptivemask": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp]),
+    "repet_beatspectrogram": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "repet_periods": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "repet_stft": (_c_int, [_vp, _vp, _c_int, _c_i64, _vp, _vp, _vp]),
     "repet_istft": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_double, _vp]),
     "repet_beatspectrum": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
@@ -221,8 +231,10 @@ def hamming_window(window_length):
     return scipy.signal.windows.hamming(window_length, sym=False)
 
 
-def derive_params(sampling_frequency, tunables):
-    """All derived integers of the five drivers."""
+def derive_params(sampling_frequency, tunables, driver="original"):
+    """All derived integers of the five drivers.  `driver` selects the
+    unit of the segment sizes: samples for extended (repet.py:266-267), frames for adaptive
+    (repet.py:519-520)."""
     window_length = pow(2, int(np.ceil(np.log2(0.04 * sampling_frequency))))  # repet.py:130
     step_length = int(window_length / 2)  # repet.py:132
     window_function = hamming_window(window_length)
@@ -240,6 +252,12 @@ def derive_params(sampling_frequency, tunables):
     p.similarity_threshold = float(tunables["similarity_threshold"])
     p.buffer_frames = int(round((tunables["buffer_length"] * sampling_frequency) / step_length))  # :787
     p.cola_gain = float(sum(window_function[0:window_length:step_length]))  # repet.py:1103
+    if driver == "extended":
+        p.segment_length = round(tunables["segment_length"] * sampling_frequency)  # repet.py:266
+        p.segment_step = round(tunables["segment_step"] * sampling_frequency)  # repet.py:267
+    else:
+        p.segment_length = int(round(tunables["segment_length"] * sampling_frequency / step_length))  # repet.py:519
+        p.segment_step = int(round(tunables["segment_step"] * sampling_frequency / step_length))  # repet.py:520
     return p, window_function
 
 
@@ -393,6 +411,126 @@ def mask(audio_spectrogram, repeating_period, handle=None):
     return out.T.astype(np.float64)
 
 
+def _single_f64(entry, driver, audio_signal, sampling_frequency, tunables, handle, ints_capacity):
+    number_samples, number_channels = np.shape(audio_signal)  # ValueError if not 2-D, as in the reference
+    handle = handle or get_handle()
+    params, _ = derive_params(sampling_frequency, tunables, driver)
+    handle.ensure_window(params.window_length)
+    audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
+    background = np.empty((number_samples, number_channels), dtype=np.float64)
+    capacity = ints_capacity(params, number_samples)
+    ints = np.zeros(max(1, capacity), dtype=np.int32)
+    handle.check(
+        getattr(handle.lib, entry)(
+            handle.h, _ptr(audio), number_samples, number_channels, ctypes.byref(params), _ptr(background), _ptr(ints),
+            len(ints),
+        )
+    )
+    return background, ints[:capacity]
+
+
+def extended_f64(audio_signal, sampling_frequency, tunables, handle=None, return_periods=False):
+    """repet.extended with the reference's calling convention (repet.py:205-419)."""
+    lib = load_library()
+    background, periods = _single_f64(
+        "repet_extended_f64", "extended", audio_signal, sampling_frequency, tunables, handle,
+        lambda params, number_samples: lib.repet_extended_segments(ctypes.byref(params), number_samples),
+    )
+    return (background, periods) if return_periods else background
+
+
+def adaptive_f64(audio_signal, sampling_frequency, tunables, handle=None, return_periods=False):
+    """repet.adaptive with the reference's calling convention (repet.py:422-568)."""
+    background, periods = _single_f64(
+        "repet_adaptive_f64", "adaptive", audio_signal, sampling_frequency, tunables, handle,
+        lambda params, number_samples: number_of_frames(number_samples, params.window_length, params.step_length),
+    )
+    return (background, periods) if return_periods else background
+
+
+def driver_batch(driver, audio, sampling_frequency, tunables, handle=None):
+    """original / extended / adaptive over a batch: audio (B, C, S) float32 planar host memory.
+    Returns (background (B, C, S) float32, integer outputs (B, ints_per_clip) int32)."""
+    handle = handle or get_handle()
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    if audio.ndim != 3:
+        raise ValueError("audio must have shape (clips, channels, samples)")
+    number_clips, number_channels, number_samples = audio.shape
+    params, _ = derive_params(sampling_frequency, tunables, driver)
+    handle.ensure_window(params.window_length)
+    if driver == "original":
+        per_clip = 1
+    elif driver == "extended":
+        per_clip = handle.lib.repet_extended_segments(ctypes.byref(params), number_samples)
+    elif driver == "adaptive":
+        per_clip = number_of_frames(number_samples, params.window_length, params.step_length)
+    else:
+        raise ValueError("unknown driver %r" % driver)
+    background = np.empty_like(audio)
+    ints = np.zeros((number_clips, max(1, per_clip)), dtype=np.int32)
+    handle.check(
+        getattr(handle.lib, "repet_%s_batch" % driver)(
+            handle.h, _ptr(audio), number_clips, number_channels, number_samples, ctypes.byref(params), _ptr(background),
+            _ptr(ints),
+        )
+    )
+    return background, ints
+
+
+def beatspectrogram(audio_spectrogram, segment_length, segment_step, handle=None):
+    """_beatspectrogram (repet.py:1161-1206): (F, T) -> float64 (segment_length, T).  The device
+    computes the beat spectrum of every segment; the column replication (including the all-zero
+    column i+step-1, quirk Q3) is pure data movement and happens here."""
+    handle = handle or get_handle()
+    spectrogram = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
+    number_times, number_rows = spectrogram.shape
+    number_segments = -(-number_times // segment_step)
+    beat = np.empty((number_segments, segment_length), dtype=np.float64)
+    count = ctypes.c_int32(0)
+    handle.check(
+        handle.lib.repet_beatspectrogram(
+            handle.h, _ptr(spectrogram), number_times, number_rows, int(segment_length), int(segment_step), _ptr(beat),
+            ctypes.byref(count),
+        )
+    )
+    assert count.value == number_segments
+    beat_spectrogram = np.zeros((segment_length, number_times))
+    for index, i in enumerate(range(0, number_times, segment_step)):
+        beat_spectrogram[:, i] = beat[index]
+        beat_spectrogram[:, i : min(i + segment_step - 1, number_times)] = beat[index][:, np.newaxis]
+    return beat_spectrogram
+
+
+def periods(beat_spectrogram, period_range, handle=None):
+    """_periods (repet.py:1249-1291): 1-D beat spectrum -> int, 2-D beat spectrogram -> int array."""
+    handle = handle or get_handle()
+    beat = np.ascontiguousarray(beat_spectrogram, dtype=np.float64)
+    one_dimensional = beat.ndim == 1
+    matrix = beat.reshape(beat.shape[0], -1)
+    out = np.zeros(matrix.shape[1], dtype=np.int32)
+    handle.check(
+        handle.lib.repet_periods(
+            handle.h, _ptr(matrix), matrix.shape[0], matrix.shape[1], int(period_range[0]), int(period_range[1]), _ptr(out)
+        )
+    )
+    return int(out[0]) if one_dimensional else out.astype(np.int64)
+
+
+def adaptivemask(audio_spectrogram, repeating_periods, filter_order, handle=None):
+    """_adaptivemask (repet.py:1461-1508): (1025, T) magnitudes, per-frame periods -> float64 (1025, T)."""
+    handle = handle or get_handle()
+    magnitude = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
+    number_times, number_frequencies = magnitude.shape
+    if number_frequencies != 1025:
+        raise NotImplementedError("this build masks 1025-bin spectrograms (window_length 2048)")
+    per = np.ascontiguousarray(repeating_periods, dtype=np.int32)
+    if per.shape != (number_times,):
+        raise ValueError("one period per time frame expected")
+    out = np.empty((number_times, number_frequencies), dtype=np.float32)
+    handle.check(handle.lib.repet_adaptivemask(handle.h, _ptr(magnitude), number_times, _ptr(per), int(filter_order), _ptr(out)))
+    return out.T.astype(np.float64)
+
+
 def _not_built(name):
     def raiser(*args, **kwargs):
         raise NotImplementedError("repet.%s has no CUDA path in this build yet (there is no CPU fallback)" % name)
@@ -400,7 +538,5 @@ def _not_built(name):
     return raiser
 
 
-extended_f64 = _not_built("extended")
-adaptive_f64 = _not_built("adaptive")
 sim_f64 = _not_built("sim")
 simonline_f64 = _not_built("simonline")
