@@ -76,7 +76,7 @@ const char* repet_version(void);
 /* Per-kernel device time for the roofline report: with profiling on, every launch is
  * bracketed by a CUDA event pair on the handle's stream.  repet_profile_read synchronises the
  * stream and returns accumulated milliseconds and launch counts per kernel id. */
-#define REPET_NUM_KERNELS 8
+#define REPET_NUM_KERNELS 12
 #define REPET_K_STFT 0
 #define REPET_K_BEAT 1
 #define REPET_K_PERIODS 2
@@ -84,6 +84,9 @@ const char* repet_version(void);
 #define REPET_K_MASK_ISTFT 4
 #define REPET_K_CONVERT 5
 #define REPET_K_XFADE 6
+#define REPET_K_NORMALIZE 7
+#define REPET_K_SIMGEMM 8
+#define REPET_K_TOPK 9
 /* Process-wide launch-shape knobs for experiments: "stft_minb", "mask_minb" (resident CTAs per SM
  * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic). */
 int repet_set_tuning(const char* name, int value);
@@ -126,6 +129,33 @@ int repet_adaptive_batch(repet_handle* h, const float* audio, int n_clips, int n
                          const repet_params* p, float* background, int32_t* periods_host);
 int repet_adaptive_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                        double* background, int32_t* periods_host, int periods_capacity);
+
+/* repet.sim (repet.py:571-709): cosine self-similarity of the channel-mean magnitude frames,
+ * per-frame lists of the most similar frames (strict local maxima within +-similarity_distance
+ * frames, >= similarity_threshold, best similarity_number by value), median over each list.
+ * The fast similarity matrix only proposes candidates; every decision is certified with exact
+ * float64 dot products.  Integer output per clip: [counts n_frames][indices n_frames x number]
+ * (n_frames = the centred frame count; list i holds counts[i] valid frame indices, most similar
+ * first). */
+int repet_sim_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                        const repet_params* p, float* background, int32_t* lists_dev, int32_t* lists_host);
+int repet_sim_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                    const repet_params* p, float* background, int32_t* lists_host);
+int repet_sim_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                  double* background, int32_t* lists_host, int lists_capacity);
+
+/* repet.simonline (repet.py:712-911): every frame j >= buffer_frames-1 against the previous
+ * buffer_frames-1 frames in ring-buffer slot order; frames are NOT centred and earlier frames are
+ * never synthesised.  All frames are independent, so the whole signal is processed in parallel.
+ * Integer output per clip as for repet_sim with n_frames = repet_simonline_frames(p, n_samples);
+ * lists hold FRAME indices. */
+int repet_simonline_frames(const repet_params* p, int64_t n_samples);
+int repet_simonline_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                              const repet_params* p, float* background, int32_t* lists_dev, int32_t* lists_host);
+int repet_simonline_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                          const repet_params* p, float* background, int32_t* lists_host);
+int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                        double* background, int32_t* lists_host, int lists_capacity);
 
 /* ---- helpers (unit parity with the reference's private functions), HOST pointers -------- */
 /* _stft (repet.py:1001-1060) of n_channels (1 or 2) real signals at once.

@@ -14,8 +14,8 @@ namespace {
 const double kPi = 3.14159265358979323846264338327950288;
 const int FFT_N_HOST = 2048;
 
-const char* kKernelNames[REPET_NUM_KERNELS] = {"k_stft", "k_beat", "k_periods", "k_model", "k_mask_istft",
-                                               "k_convert", "k_xfade", "k_other7"};
+const char* kKernelNames[REPET_NUM_KERNELS] = {"k_stft",    "k_beat",  "k_periods",   "k_model",   "k_mask_istft", "k_convert",
+                                               "k_xfade",   "k_normalize", "k_simgemm", "k_topk",       "k_other10", "k_other11"};
 
 }  // namespace
 

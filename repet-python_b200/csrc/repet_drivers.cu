@@ -10,7 +10,11 @@ using namespace repet;
 
 namespace {
 
-enum Kind { KIND_ORIGINAL = 0, KIND_EXTENDED = 1, KIND_ADAPTIVE = 2 };
+enum Kind { KIND_ORIGINAL = 0, KIND_EXTENDED = 1, KIND_ADAPTIVE = 2, KIND_SIM = 3, KIND_SIMONLINE = 4 };
+
+// rigorous bound on |fp32 similarity - exact|: sequential fp32 accumulation of 1025 products of unit
+// vectors (gamma_n = n u ~ 6e-5) plus the fp32 rounding of the operands
+constexpr float TAU_FP32_GEMM = 1e-4f;
 
 // ---------------------------------------------------------------------------------------------
 // the period pipeline shared by `original` and the segments of `extended`:
@@ -113,6 +117,8 @@ Geom clip_geom(int n_clips, int nch, int64_t n_samples, int T) {
     g.S = (int)n_samples;
     g.T = T;
     g.item0 = 0;
+    g.frame_shift = 0;
+    g.first_frame = 0;
     return g;
 }
 
@@ -130,6 +136,8 @@ struct Plan {
     PeriodShape seg_main, seg_last;
     // adaptive (repet.py:519-520, 1174-1188)
     int seg_frames = 0, step_frames = 0, n_beat_seg = 0, left_pad = 0, lag_hi = 0, beat_parts = 0, beat_f_per_part = 0;
+    // sim / simonline
+    int number = 0, distance = 0, buffer_frames = 0;
     int ints_per_clip = 1;
     size_t bytes_per_clip = 0;
 };
@@ -201,7 +209,124 @@ int make_plan(repet_handle* h, int kind, const repet_params* p, int nch, int64_t
         plan->bytes_per_clip = b;
         return REPET_OK;
     }
+    if (kind == KIND_SIM || kind == KIND_SIMONLINE) {
+        if (p->similarity_number < 1) return fail(h, REPET_E_INVALID_ARG, "similarity_number must be at least 1");
+        if (p->similarity_distance < 0) return fail(h, REPET_E_INVALID_ARG, "similarity_distance must not be negative");
+        plan->number = p->similarity_number;
+        plan->distance = p->similarity_distance;
+        int T = plan->T;
+        if (kind == KIND_SIMONLINE) {
+            const int B = p->buffer_frames;
+            if (B < 1) return fail(h, REPET_E_INVALID_ARG, "buffer_length must cover at least one frame");
+            // the reference's warm-up loop multiplies a truncated slice by the window (repet.py:801-804)
+            if (S < WIN_N || (int64_t)(B - 2) * HOP + WIN_N > S)
+                return fail(h, REPET_E_INVALID_ARG,
+                            "operands could not be broadcast together (signal shorter than the buffer)");
+            T = (int)((S - WIN_N + HOP - 1) / HOP) + 1;  // repet.py:781, frames are not centred
+            plan->T = T;
+            plan->buffer_frames = B;
+        }
+        plan->ints_per_clip = T * (plan->number + 1);
+        size_t b = 0;
+        b += align_up((size_t)T * nch * XPITCH * sizeof(float2));   // X
+        b += align_up((size_t)T * PPITCH * sizeof(float));          // V = mean_c |X|
+        b += align_up((size_t)T * APITCH64 * sizeof(double));       // An64
+        b += align_up((size_t)T * plan->number * sizeof(int32_t));  // idx
+        b += align_up((size_t)T * sizeof(int32_t));                 // cnt
+        b += align_up((size_t)nch * T * PPITCH * sizeof(float));    // model
+        if (kind == KIND_SIM) {
+            b += align_up((size_t)T * KPAD * sizeof(float));  // An32
+            b += align_up((size_t)T * T * sizeof(float));     // S
+        }
+        b += 2048;
+        plan->bytes_per_clip = b;
+        return REPET_OK;
+    }
     return fail(h, REPET_E_INVALID_ARG, "unknown driver kind");
+}
+
+// idx/cnt (item-major workspace arrays) -> the ABI's per-clip layout [cnt T][idx T*number]
+int scatter_lists(repet_handle* h, const Plan& plan, int g, const int32_t* idx, const int32_t* cnt, int32_t* ints) {
+    const int T = plan.T;
+    const size_t ipc = (size_t)plan.ints_per_clip * sizeof(int32_t);
+    CU(cudaMemcpy2DAsync(ints, ipc, cnt, (size_t)T * sizeof(int32_t), (size_t)T * sizeof(int32_t), g,
+                         cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(ints + T, ipc, idx, (size_t)T * plan.number * sizeof(int32_t),
+                         (size_t)T * plan.number * sizeof(int32_t), g, cudaMemcpyDeviceToDevice, h->stream));
+    return REPET_OK;
+}
+
+int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, float* out, int32_t* ints,
+            unsigned char* ws, size_t ws_bytes) {
+    const int nch = plan.nch, T = plan.T;
+    const bool online = plan.kind == KIND_SIMONLINE;
+    const int G = (int)std::min<size_t>(std::min<size_t>((size_t)n_clips, MAX_ITEMS_PER_LAUNCH / 2),
+                                        std::max<size_t>(1, ws_bytes / plan.bytes_per_clip));
+    const float scale = (float)(1.0 / ((double)WIN_N * plan.p.cola_gain));
+    cudaStream_t st = h->stream;
+    for (int clip0 = 0; clip0 < n_clips; clip0 += G) {
+        const int g = std::min(G, n_clips - clip0);
+        Bump bump(ws);
+        float2* X = bump.take<float2>((size_t)g * T * nch * XPITCH);
+        float* V = bump.take<float>((size_t)g * T * PPITCH);
+        double* An64 = bump.take<double>((size_t)g * T * APITCH64);
+        int32_t* idx = bump.take<int32_t>((size_t)g * T * plan.number);
+        int32_t* cnt = bump.take<int32_t>((size_t)g * T);
+        float* model = bump.take<float>((size_t)g * nch * T * PPITCH);
+        int32_t* overflow = bump.take<int32_t>(1);
+        float* An32 = online ? nullptr : bump.take<float>((size_t)g * T * KPAD);
+        float* S = online ? nullptr : bump.take<float>((size_t)g * T * T);
+        Geom geom = clip_geom(g, nch, plan.S, T);
+        geom.first_offset = (long long)clip0 * geom.clip_stride;
+        if (online) {
+            geom.frame_shift = 1;
+            geom.first_frame = plan.buffer_frames - 1;
+        }
+        const int K = pick_frames_per_cta(h, (long long)g * T);
+        {
+            Timed timed(h, REPET_K_STFT);
+            launch_stft(st, audio, geom, nch, h->window, tables(h), X, V, P_MAGNITUDE, K);
+        }
+        {
+            Timed timed(h, REPET_K_NORMALIZE);
+            launch_normalize(st, V, g * T, An64, An32);
+        }
+        CU(cudaMemsetAsync(cnt, 0, (size_t)g * T * sizeof(int32_t), st));
+        if (online) {
+            Timed timed(h, REPET_K_TOPK);
+            launch_online_select(st, An64, g, T, plan.buffer_frames, plan.p.similarity_threshold, plan.distance,
+                                 plan.number, idx, cnt);
+        } else {
+            {
+                Timed timed(h, REPET_K_SIMGEMM);
+                launch_selfsim_simt(st, An32, g, T, S);
+            }
+            CU(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+            Timed timed(h, REPET_K_TOPK);
+            if (launch_topk(st, S, An64, g, T, TAU_FP32_GEMM, plan.p.similarity_threshold, plan.distance, plan.number,
+                            idx, cnt, overflow))
+                return fail(h, REPET_E_UNSUPPORTED, "track too long for the in-shared-memory similarity row");
+        }
+        {
+            Timed timed(h, REPET_K_MODEL);
+            if (launch_simmodel(st, X, g, T, nch, idx, cnt, plan.number, geom.first_frame, model))
+                return fail(h, REPET_E_UNSUPPORTED, "similarity_number too large for the shared-memory median");
+        }
+        {
+            Timed timed(h, REPET_K_MASK_ISTFT);
+            launch_mask_istft(st, X, geom, nch, nullptr, T, model, plan.p.cutoff_bins, scale, tables(h), out, K);
+        }
+        int rc = scatter_lists(h, plan, g, idx, cnt, ints + (size_t)clip0 * plan.ints_per_clip);
+        if (rc) return rc;
+        if (!online) {
+            int32_t flag = 0;
+            CU(cudaMemcpyAsync(&flag, overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (flag) return fail(h, REPET_E_UNSUPPORTED, "too many near-tied similarity candidates in one column");
+        }
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
 }
 
 int run_extended(repet_handle* h, const Plan& plan, const float* audio, int n_clips, float* out, int32_t* ints,
@@ -306,7 +431,8 @@ int run_plan(repet_handle* h, const Plan& plan, const float* audio, int n_clips,
         return period_pipeline(h, audio, g, out, g, plan.nch, &plan.p, plan.whole, ints, ws, ws_bytes);
     }
     if (plan.kind == KIND_EXTENDED) return run_extended(h, plan, audio, n_clips, out, ints, ws, ws_bytes);
-    return run_adaptive(h, plan, audio, n_clips, out, ints, ws, ws_bytes);
+    if (plan.kind == KIND_ADAPTIVE) return run_adaptive(h, plan, audio, n_clips, out, ints, ws, ws_bytes);
+    return run_sim(h, plan, audio, n_clips, out, ints, ws, ws_bytes);
 }
 
 int chunk_clips(repet_handle* h, const Plan& plan, int n_clips) {
@@ -482,6 +608,38 @@ int repet_adaptive_batch(repet_handle* h, const float* audio, int n_clips, int n
 int repet_adaptive_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                        double* background, int32_t* periods_host, int periods_capacity) {
     return single_f64(h, KIND_ADAPTIVE, audio, n_samples, n_channels, p, background, periods_host, periods_capacity);
+}
+
+// ---- repet.sim (repet.py:571-709) ----------------------------------------------------------
+int repet_sim_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                        const repet_params* p, float* background, int32_t* lists_dev, int32_t* lists_host) {
+    return batch_dev(h, KIND_SIM, audio, n_clips, n_channels, n_samples, p, background, lists_dev, lists_host, nullptr);
+}
+int repet_sim_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                    const repet_params* p, float* background, int32_t* lists_host) {
+    return batch_host(h, KIND_SIM, audio, n_clips, n_channels, n_samples, p, background, lists_host);
+}
+int repet_sim_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                  double* background, int32_t* lists_host, int lists_capacity) {
+    return single_f64(h, KIND_SIM, audio, n_samples, n_channels, p, background, lists_host, lists_capacity);
+}
+
+// ---- repet.simonline (repet.py:712-911) ----------------------------------------------------
+int repet_simonline_frames(const repet_params* p, int64_t n_samples) {
+    if (!p || n_samples < p->window_length) return 0;
+    return (int)((n_samples - p->window_length + p->step_length - 1) / p->step_length) + 1;
+}
+int repet_simonline_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                              const repet_params* p, float* background, int32_t* lists_dev, int32_t* lists_host) {
+    return batch_dev(h, KIND_SIMONLINE, audio, n_clips, n_channels, n_samples, p, background, lists_dev, lists_host, nullptr);
+}
+int repet_simonline_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                          const repet_params* p, float* background, int32_t* lists_host) {
+    return batch_host(h, KIND_SIMONLINE, audio, n_clips, n_channels, n_samples, p, background, lists_host);
+}
+int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
+                        double* background, int32_t* lists_host, int lists_capacity) {
+    return single_f64(h, KIND_SIMONLINE, audio, n_samples, n_channels, p, background, lists_host, lists_capacity);
 }
 
 }  // extern "C"

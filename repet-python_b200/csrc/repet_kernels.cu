@@ -50,11 +50,11 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
     int par = 0;
     for (int j = j0; j < j1; ++j) {
         float2 r[16];
-        const long long base = (long long)(j - 1) * HOP + t;
+        const long long base = (long long)(j - 1 + g.frame_shift) * HOP + t;
         const bool carry = j > j0;
         // pull the next frame's new half (2 x 4 KB) towards L2 while this frame is transformed
         if (t < 64 && j + 1 < j1) {
-            const long long nxt = (long long)(j + 1) * HOP + (t & 31) * 32;
+            const long long nxt = (long long)(j + 1 + g.frame_shift) * HOP + (t & 31) * 32;
             if (nxt < g.S) prefetch_l2((t < 32 || NCH == 1 ? a0 : a1) + nxt);
         }
 #pragma unroll
@@ -490,7 +490,8 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     const int t = threadIdx.x;
     const int item = blockIdx.y;
     const int b0 = blockIdx.x * nblk;               // first output block
-    const int b1 = min(b0 + nblk, g.T - 1);         // one past the last output block
+    const int n_centred = g.T + g.frame_shift;      // centred frame count (X has g.T rows)
+    const int b1 = min(b0 + nblk, n_centred - 1);   // one past the last output block
     s_tw2[t] = tb.tw2[t];
     Twiddle1 tw;
     tw.load(tb.tw1, t);
@@ -505,7 +506,14 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     for (int i = 0; i < 8; ++i) carry_l[i] = carry_r[i] = 0.f;
     __syncthreads();
     int par = 0;
-    for (int j = b0; j <= b1; ++j) {
+    for (int jc = b0; jc <= b1; ++jc) {
+        const int j = jc - g.frame_shift;  // row of X / of the model
+        float2 r[16];
+        if (j < g.first_frame || j >= g.T) {
+            // a frame that does not exist (online: before the buffer is full): contributes zeros
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = make_float2(0.f, 0.f);
+        } else {
         float2* A = s_buf[par];
         float2* B = s_buf[par ^ 1];
         const float2* __restrict__ xl_row = X + ((size_t)item * g.T + j) * (size_t)(NCH * XPITCH);
@@ -518,7 +526,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
         }
         // pull the next frame's spectra (NCH x 8 KB) towards L2 while this frame is processed
-        if (j < b1 && t < 64 * NCH) prefetch_l2(xl_row + (size_t)(NCH * XPITCH) + t * 16);
+        if (jc < b1 && j + 1 < g.T && t < 64 * NCH) prefetch_l2(xl_row + (size_t)(NCH * XPITCH) + t * 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int k = t + 128 * i;
@@ -555,7 +563,6 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             }
         }
         __syncthreads();
-        float2 r[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) r[n1] = A[n1 * 128 + t];
         fft_stage1(r, tw, B, t);
@@ -563,9 +570,11 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
         fft_stage2(r, B, A, s_tw2, t);
         __syncthreads();
         fft_stage3(r, A, t);
+        par ^= 1;
+        }
         // r[h*8+k3] = (N*yR, N*yL) at frame sample n = (t + 128h) + 256*k3
-        if (j > b0) {
-            const long long blk = (long long)(j - 1) * HOP;
+        if (jc > b0) {
+            const long long blk = (long long)(jc - 1) * HOP;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -584,13 +593,12 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
                 carry_l[h * 4 + k3] = r[h * 8 + 4 + k3].y;
                 carry_r[h * 4 + k3] = r[h * 8 + 4 + k3].x;
             }
-        par ^= 1;
     }
 }
 
 void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const int* period, int pmax,
                        const float* model, int cutoff, float scale, FftTables tb, float* out, int blocks_per_cta) {
-    const int nblocks = g.T - 1;
+    const int nblocks = g.T + g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
 #define REPET_GO(NCH, MINB) \
     k_mask_istft<NCH, true, MINB><<<grid, FFT_THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
@@ -606,7 +614,7 @@ void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const 
 
 void launch_istft(cudaStream_t st, const float2* X, Geom g, int nch, float scale, FftTables tb, float* out,
                   int blocks_per_cta) {
-    const int nblocks = g.T - 1;
+    const int nblocks = g.T + g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
     if (nch == 2)
         k_mask_istft<2, false, 4><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);

@@ -12,6 +12,8 @@ constexpr int XPITCH = WIN_N / 2;  // float2 per (frame, channel): bin 0 holds (
 constexpr int PPITCH = 1032;       // floats per frame row of P / model (1025 rounded up to 32 B)
 constexpr int BEAT_L = 2048;       // FFT length of the beat-spectrum transforms
 constexpr int MAX_MEDIAN_REGS = 32;  // sorting-network path handles up to 32 gathered values
+constexpr int KPAD = 1056;           // K of the similarity GEMM operand: 1025 zero-padded to 33 x 32 floats
+constexpr int APITCH64 = 1032;       // doubles per row of the float64-normalised frames
 
 // A batch of equally long items cut out of planar audio [clip][channel][sample]:
 // item = clip * seg_per_clip + seg starts at clip*clip_stride + seg*seg_stride (+ c*chan_stride).
@@ -26,6 +28,11 @@ struct Geom {
     int S;                   // samples per item
     int T;                   // STFT frames per item
     int item0;               // global index of this launch's first item (workspace indices are local)
+    // Online REPET-SIM frames are not centred (repet.py:781, 834-901): frame j covers samples
+    // [j*H, j*H + N).  frame_shift = 1 maps the kernels' centred frame index jc to row jc - 1, and
+    // rows below first_frame are never synthesised (quirk Q5).  Centred drivers use 0, 0.
+    int frame_shift;
+    int first_frame;
 };
 
 struct FftTables {
@@ -86,6 +93,16 @@ void launch_xfade(cudaStream_t st, const float* seg_main, const float* seg_last,
 // _periods on caller-provided float64 beat spectra
 void launch_argmax_columns(cudaStream_t st, const double* beat, int n_lags, int n_columns, int lag_lo, int lag_hi,
                            int* period);
+
+// REPET-SIM (repet_sim.cu)
+void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32);
+void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);
+int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
+                int number, int* idx_out, int* cnt_out, int* overflow);
+void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, double thr, int d, int number,
+                          int* idx_out, int* cnt_out);
+int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* idx, const int* cnt,
+                    int number, int first_frame, float* model);
 
 // layout converters for the float64 (S, C) NumPy convention of the reference API
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out);

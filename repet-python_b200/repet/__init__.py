@@ -108,6 +108,12 @@ def adaptive_batch(audio_signals, sampling_frequency):
     return _host.driver_batch("adaptive", audio_signals, sampling_frequency, _tunables())
 
 
+def sim_batch(audio_signals, sampling_frequency):
+    """REPET-SIM over a batch (see original_batch); lists: int32 (number_clips, number_times*(similarity_number+1)),
+    per clip [counts][indices] -- repet._host.unpack_lists turns a row into the reference's ragged list."""
+    return _host.driver_batch("sim", audio_signals, sampling_frequency, _tunables())
+
+
 def extended(audio_signal, sampling_frequency):
     """Compute REPET extended (repet.py:205-419)."""
     return _host.extended_f64(audio_signal, sampling_frequency, _tunables())

@@ -83,6 +83,13 @@ SIGNATURES = {
     "repet_adaptivemask": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp]),
     "repet_beatspectrogram": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "repet_periods": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "repet_sim_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
+    "repet_sim_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_sim_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
+    "repet_simonline_frames": (_c_int, [_pp, _c_i64]),
+    "repet_simonline_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
+    "repet_simonline_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_simonline_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
     "repet_stft": (_c_int, [_vp, _vp, _c_int, _c_i64, _vp, _vp, _vp]),
     "repet_istft": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_double, _vp]),
     "repet_beatspectrum": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
@@ -192,11 +199,11 @@ class Handle:
 
     def profile_read(self, reset=True):
         """{kernel name: (total ms, launches)} accumulated while profiling was on."""
-        ms = np.zeros(8, dtype=np.float64)
-        counts = np.zeros(8, dtype=np.uint64)
+        ms = np.zeros(12, dtype=np.float64)
+        counts = np.zeros(12, dtype=np.uint64)
         self.check(self.lib.repet_profile_read(self.h, _ptr(ms), _ptr(counts), 1 if reset else 0))
         return {
-            self.lib.repet_kernel_name(i).decode(): (float(ms[i]), int(counts[i])) for i in range(8) if counts[i]
+            self.lib.repet_kernel_name(i).decode(): (float(ms[i]), int(counts[i])) for i in range(12) if counts[i]
         }
 
 
@@ -464,6 +471,12 @@ def driver_batch(driver, audio, sampling_frequency, tunables, handle=None):
         per_clip = handle.lib.repet_extended_segments(ctypes.byref(params), number_samples)
     elif driver == "adaptive":
         per_clip = number_of_frames(number_samples, params.window_length, params.step_length)
+    elif driver == "sim":
+        per_clip = number_of_frames(number_samples, params.window_length, params.step_length) * (params.similarity_number + 1)
+    elif driver == "simonline":
+        per_clip = max(0, handle.lib.repet_simonline_frames(ctypes.byref(params), number_samples)) * (
+            params.similarity_number + 1
+        )
     else:
         raise ValueError("unknown driver %r" % driver)
     background = np.empty_like(audio)
@@ -531,12 +544,42 @@ def adaptivemask(audio_spectrogram, repeating_periods, filter_order, handle=None
     return out.T.astype(np.float64)
 
 
-def _not_built(name):
-    def raiser(*args, **kwargs):
-        raise NotImplementedError("repet.%s has no CUDA path in this build yet (there is no CPU fallback)" % name)
+def unpack_lists(ints, number_frames, number):
+    """[counts T][indices T x number] (the ABI's per-clip layout) -> list of T int arrays."""
+    counts = ints[:number_frames]
+    table = ints[number_frames : number_frames * (number + 1)].reshape(number_frames, number)
+    return [table[i, : counts[i]].astype(np.int64) for i in range(number_frames)]
 
-    return raiser
+
+def sim_f64(audio_signal, sampling_frequency, tunables, handle=None, return_indices=False):
+    """repet.sim with the reference's calling convention (repet.py:571-709)."""
+    number = int(tunables["similarity_number"])
+    frames = {}
+
+    def capacity(params, number_samples):
+        frames["T"] = number_of_frames(number_samples, params.window_length, params.step_length)
+        return frames["T"] * (number + 1)
+
+    background, ints = _single_f64("repet_sim_f64", "sim", audio_signal, sampling_frequency, tunables, handle, capacity)
+    if return_indices:
+        return background, unpack_lists(ints, frames["T"], number)
+    return background
 
 
-sim_f64 = _not_built("sim")
-simonline_f64 = _not_built("simonline")
+def simonline_f64(audio_signal, sampling_frequency, tunables, handle=None, return_indices=False):
+    """repet.simonline with the reference's calling convention (repet.py:712-911).  With
+    return_indices the lists of frames >= buffer_frames-1 hold FRAME indices (most similar first)."""
+    lib = load_library()
+    number = int(tunables["similarity_number"])
+    frames = {}
+
+    def capacity(params, number_samples):
+        frames["T"] = max(0, lib.repet_simonline_frames(ctypes.byref(params), number_samples))
+        return frames["T"] * (number + 1)
+
+    background, ints = _single_f64(
+        "repet_simonline_f64", "simonline", audio_signal, sampling_frequency, tunables, handle, capacity
+    )
+    if return_indices:
+        return background, unpack_lists(ints, frames["T"], number)
+    return background

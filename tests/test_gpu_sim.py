@@ -1,0 +1,97 @@
+"""GPU: repet.sim and repet.simonline against the oracle and the golden vectors recorded from the
+reference: similar-frame lists bit-exact (set AND order), signals within 1e-4 relative."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+import make_golden
+import repet_oracle as oracle
+import repet_synth
+
+pytestmark = pytest.mark.gpu
+
+FS = 44100
+RTOL_SIGNAL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def repet():
+    import repet as module
+
+    module._host.get_handle(0)
+    return module
+
+
+def _assert_signal(y, y_ref, what):
+    assert y.shape == y_ref.shape, what
+    rel = float(np.linalg.norm(np.ravel(y - y_ref)) / max(np.linalg.norm(np.ravel(y_ref)), 1e-300))
+    worst = float(np.max(np.abs(y - y_ref)) / max(np.max(np.abs(y_ref)), 1e-300))
+    assert rel <= RTOL_SIGNAL and worst <= RTOL_SIGNAL, "%s: rel L2 %.3e, max-abs/max %.3e" % (what, rel, worst)
+
+
+def _assert_lists(lists, counts_ref, flat_ref, what, first=0):
+    counts = np.array([len(v) for v in lists[first:]])
+    assert np.array_equal(counts, counts_ref), "%s: list lengths differ in %d frames" % (what, int(np.sum(counts != counts_ref)))
+    flat = np.concatenate(lists[first:]) if len(lists) > first else np.array([], dtype=np.int64)
+    assert np.array_equal(flat, flat_ref), "%s: %d of %d indices differ" % (what, int(np.sum(flat != flat_ref)), len(flat_ref))
+
+
+@pytest.mark.parametrize("case", ["wav_5s", "synth_12s", "synth_mono_8s", "wav_full"])
+def test_sim_matches_reference(repet, case, golden_drivers, wav_pcm):
+    warnings.simplefilter("ignore")
+    x = make_golden.case_input(make_golden.DRIVER_CASES[case], wav_pcm)
+    y, lists = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    key = "%s/sim" % case
+    _assert_lists(lists, golden_drivers[key + "/index_counts"], golden_drivers[key + "/index_flat"], key)
+    _assert_signal(y[:: make_golden.DECIMATE], golden_drivers[key + "/dec"], key + " (golden)")
+    assert np.array_equal(repet.sim(x, FS), y)
+
+
+def test_sim_long_lists_and_tunables(repet):
+    """distance 0.1 s and threshold 0.5: hundreds of local maxima per column, the top-`number` cap
+    binds, and lists longer than 32 frames take the shared-memory median path."""
+    x = make_golden.case_input(make_golden.DRIVER_CASES["synth_21s"])
+    saved = (repet.similarity_distance, repet.similarity_threshold, repet.similarity_number)
+    try:
+        repet.similarity_distance, repet.similarity_threshold, repet.similarity_number = 0.1, 0.5, 60
+        y, lists = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+        y_ref, det = oracle.sim(x, FS, return_details=True, similarity_distance=0.1, similarity_threshold=0.5,
+                                similarity_number=60)
+    finally:
+        repet.similarity_distance, repet.similarity_threshold, repet.similarity_number = saved
+    ref_lists = det["indices"]
+    assert max(len(v) for v in ref_lists) == 60  # the cap binds
+    _assert_lists(lists, np.array([len(v) for v in ref_lists]), np.concatenate(ref_lists), "sim tunables")
+    _assert_signal(y, y_ref, "sim tunables")
+
+
+@pytest.mark.parametrize("case", ["synth_12s", "wav_full"])
+def test_simonline_matches_reference(repet, case, golden_drivers, wav_pcm):
+    warnings.simplefilter("ignore")
+    x = make_golden.case_input(make_golden.DRIVER_CASES[case], wav_pcm)
+    y, lists = repet._host.simonline_f64(x, FS, repet._tunables(), return_indices=True)
+    key = "%s/simonline" % case
+    first = int(golden_drivers[key + "/first_frame"])
+    _assert_lists(lists, golden_drivers[key + "/index_counts"], golden_drivers[key + "/index_flat"], key, first=first)
+    _assert_signal(y[:: make_golden.DECIMATE], golden_drivers[key + "/dec"], key + " (golden)")
+    # quirk Q5: nothing is synthesised before frame buffer_frames-1
+    assert np.all(y[: first * 1024] == 0)
+    assert np.array_equal(repet.simonline(x, FS), y)
+
+
+def test_simonline_too_short_raises(repet):
+    with pytest.raises(ValueError):
+        repet.simonline(np.full((5 * FS, 2), 0.01), FS)
+
+
+def test_sim_batch_matches_single_calls(repet):
+    audio = repet_synth.make_batch(600, 3, 9 * FS)
+    background, ints = repet.sim_batch(audio, FS)
+    T = oracle.number_of_frames(9 * FS, 2048, 1024)
+    for i in range(audio.shape[0]):
+        y_ref, det = oracle.sim(audio[i].T.astype(np.float64), FS, return_details=True)
+        lists = repet._host.unpack_lists(ints[i], T, 100)
+        _assert_lists(lists, np.array([len(v) for v in det["indices"]]), np.concatenate(det["indices"]), "clip %d" % i)
+        _assert_signal(background[i].T.astype(np.float64), y_ref, "clip %d" % i)
