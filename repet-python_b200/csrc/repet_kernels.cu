@@ -490,8 +490,10 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     const int t = threadIdx.x;
     const int item = blockIdx.y;
     const int b0 = blockIdx.x * nblk;               // first output block
-    const int n_centred = g.T + g.frame_shift;      // centred frame count (X has g.T rows)
-    const int b1 = min(b0 + nblk, n_centred - 1);   // one past the last output block
+    // output blocks: T-1 for centred frames; T+1 for online frames (frame j fills blocks j and j+1,
+    // so the last block holds the second half of the last frame alone)
+    const int n_blocks = g.T + 2 * g.frame_shift - 1;
+    const int b1 = min(b0 + nblk, n_blocks);        // one past the last output block
     s_tw2[t] = tb.tw2[t];
     Twiddle1 tw;
     tw.load(tb.tw1, t);
@@ -598,7 +600,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
 
 void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const int* period, int pmax,
                        const float* model, int cutoff, float scale, FftTables tb, float* out, int blocks_per_cta) {
-    const int nblocks = g.T + g.frame_shift - 1;
+    const int nblocks = g.T + 2 * g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
 #define REPET_GO(NCH, MINB) \
     k_mask_istft<NCH, true, MINB><<<grid, FFT_THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
@@ -614,7 +616,7 @@ void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const 
 
 void launch_istft(cudaStream_t st, const float2* X, Geom g, int nch, float scale, FftTables tb, float* out,
                   int blocks_per_cta) {
-    const int nblocks = g.T + g.frame_shift - 1;
+    const int nblocks = g.T + 2 * g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
     if (nch == 2)
         k_mask_istft<2, false, 4><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
