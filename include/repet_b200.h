@@ -88,7 +88,8 @@ const char* repet_version(void);
 #define REPET_K_SIMGEMM 8
 #define REPET_K_TOPK 9
 /* Process-wide launch-shape knobs for experiments: "stft_minb", "mask_minb" (resident CTAs per SM
- * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic). */
+ * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic), "simgemm_tc" (1 = tcgen05 similarity GEMM, 0 = fp32
+ * CUDA-core cross-check kernel). */
 int repet_set_tuning(const char* name, int value);
 int repet_set_profiling(repet_handle* h, int on);
 int repet_profile_read(repet_handle* h, double* ms, uint64_t* counts, int reset);
@@ -185,6 +186,10 @@ int repet_adaptivemask(repet_handle* h, const float* magnitude, int n_frames, co
  * every segment i = 0, step, 2 step, ... -> beat[n_segments][segment_length] float64. */
 int repet_beatspectrogram(repet_handle* h, const float* spectrogram, int n_frames, int n_rows, int segment_length,
                           int segment_step, double* beat, int32_t* n_segments_out);
+/* _selfsimilaritymatrix (repet.py:1209-1225), fast pass only: magnitudes [n_frames][n_rows<=1025]
+ * -> fp32 cosine similarity [n_frames][n_frames] (TF32 tensor-core product; the drivers certify
+ * every decision they take from it in float64). */
+int repet_selfsimilarity(repet_handle* h, const float* magnitude, int n_frames, int n_rows, float* similarity);
 /* _periods (repet.py:1249-1291) on a caller-provided beat spectrum (n_columns = 1) or beat
  * spectrogram, beat[n_lags][n_columns] row-major float64 -> periods[n_columns]. */
 int repet_periods(repet_handle* h, const double* beat, int n_lags, int n_columns, int period_lo, int period_hi,

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "librepet_b200.so")
-SOURCES = ["repet_kernels.cu", "repet_sim.cu", "repet_abi.cu", "repet_drivers.cu"]
+SOURCES = ["repet_kernels.cu", "repet_sim.cu", "repet_simgemm.cu", "repet_abi.cu", "repet_drivers.cu"]
 HEADERS = ["repet_kernels.cuh", "fft2048.cuh", "median_networks.cuh", "repet_internal.h", os.path.join("..", "..", "include", "repet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

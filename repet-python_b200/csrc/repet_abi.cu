@@ -172,6 +172,7 @@ int repet_set_tuning(const char* name, int value) {
     else if (key == "mask_minb") g_tuning.mask_minb = value;
     else if (key == "frames_per_cta") g_tuning.frames_per_cta = value;
     else if (key == "beat_parts") g_tuning.beat_parts = value;
+    else if (key == "simgemm_tc") g_tuning.simgemm_tc = value;
     else return REPET_E_INVALID_ARG;
     return REPET_OK;
 }
@@ -417,6 +418,37 @@ int repet_beatspectrogram(repet_handle* h, const float* spectrogram, int n_frame
                    nullptr, nullptr);
     h->launches += 2;
     CU(cudaMemcpyAsync(beat, b, (size_t)n_seg * segment_length * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_selfsimilarity(repet_handle* h, const float* magnitude, int n_frames, int n_rows, float* similarity) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!magnitude || !similarity || n_frames < 1 || n_rows < 1 || n_rows > NBIN)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size (n_rows <= 1025)");
+    CU(cudaSetDevice(h->device));
+    const int T = n_frames;
+    const size_t need = align_up((size_t)T * PPITCH * sizeof(float)) + align_up((size_t)T * KPAD * sizeof(float)) +
+                        align_up((size_t)T * T * sizeof(float)) + 512;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    float* V = bump.take<float>((size_t)T * PPITCH);
+    float* An32 = bump.take<float>((size_t)T * KPAD);
+    float* S = bump.take<float>((size_t)T * T);
+    cudaStream_t st = h->stream;
+    CU(cudaMemsetAsync(V, 0, (size_t)T * PPITCH * sizeof(float), st));
+    CU(cudaMemcpy2DAsync(V, PPITCH * sizeof(float), magnitude, n_rows * sizeof(float), n_rows * sizeof(float), T,
+                         cudaMemcpyHostToDevice, st));
+    launch_normalize(st, V, T, nullptr, An32, g_tuning.simgemm_tc ? 1 : 0);
+    if (g_tuning.simgemm_tc) {
+        if (launch_selfsim_tc(st, An32, 1, T, S, h->sm_count)) return fail(h, REPET_E_CUDA, "tensor-map encode failed");
+    } else {
+        launch_selfsim_simt(st, An32, 1, T, S);
+    }
+    h->launches += 2;
+    CU(cudaMemcpyAsync(similarity, S, (size_t)T * T * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     return REPET_OK;

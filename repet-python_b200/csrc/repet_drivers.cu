@@ -15,6 +15,9 @@ enum Kind { KIND_ORIGINAL = 0, KIND_EXTENDED = 1, KIND_ADAPTIVE = 2, KIND_SIM = 
 // rigorous bound on |fp32 similarity - exact|: sequential fp32 accumulation of 1025 products of unit
 // vectors (gamma_n = n u ~ 6e-5) plus the fp32 rounding of the operands
 constexpr float TAU_FP32_GEMM = 1e-4f;
+// TF32 tensor-core pass: operands rounded to nearest TF32 (2^-11 each, products of unit vectors:
+// <= 2 * 2^-11 ~ 9.8e-4) plus the fp32 accumulation of 1056 products inside the tensor core
+constexpr float TAU_TF32_GEMM = 1.5e-3f;
 
 // ---------------------------------------------------------------------------------------------
 // the period pipeline shared by `original` and the segments of `extended`:
@@ -289,7 +292,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         }
         {
             Timed timed(h, REPET_K_NORMALIZE);
-            launch_normalize(st, V, g * T, An64, An32);
+            launch_normalize(st, V, g * T, An64, An32, g_tuning.simgemm_tc ? 1 : 0);
         }
         CU(cudaMemsetAsync(cnt, 0, (size_t)g * T * sizeof(int32_t), st));
         if (online) {
@@ -299,11 +302,16 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         } else {
             {
                 Timed timed(h, REPET_K_SIMGEMM);
-                launch_selfsim_simt(st, An32, g, T, S);
+                if (g_tuning.simgemm_tc) {
+                    if (launch_selfsim_tc(st, An32, g, T, S, h->sm_count))
+                        return fail(h, REPET_E_CUDA, "tensor-map encode failed for the similarity GEMM");
+                } else {
+                    launch_selfsim_simt(st, An32, g, T, S);
+                }
             }
             CU(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
             Timed timed(h, REPET_K_TOPK);
-            if (launch_topk(st, S, An64, g, T, TAU_FP32_GEMM, plan.p.similarity_threshold, plan.distance, plan.number,
+            if (launch_topk(st, S, An64, g, T, g_tuning.simgemm_tc ? TAU_TF32_GEMM : TAU_FP32_GEMM, plan.p.similarity_threshold, plan.distance, plan.number,
                             idx, cnt, overflow))
                 return fail(h, REPET_E_UNSUPPORTED, "track too long for the in-shared-memory similarity row");
         }

@@ -48,6 +48,7 @@ struct Tuning {
     int mask_minb = 5;       // same for the mask+ISTFT kernel
     int frames_per_cta = 0;  // 0 = pick from the batch size
     int beat_parts = 0;      // 0 = pick from the batch size
+    int simgemm_tc = 1;      // 1 = tcgen05 TF32 similarity GEMM, 0 = fp32 CUDA-core cross-check kernel
 };
 extern Tuning g_tuning;
 
@@ -95,7 +96,9 @@ void launch_argmax_columns(cudaStream_t st, const double* beat, int n_lags, int 
                            int* period);
 
 // REPET-SIM (repet_sim.cu)
-void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32);
+void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, int round_tf32);
+// tcgen05 / TMEM / TMA self-similarity GEMM (repet_simgemm.cu); returns 0 on success
+int launch_selfsim_tc(cudaStream_t st, const float* An32, int n_items, int T, float* S, int sm_count);
 void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
                 int number, int* idx_out, int* cnt_out, int* overflow);

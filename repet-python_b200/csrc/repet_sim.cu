@@ -16,7 +16,7 @@ namespace repet {
 // An all-zero frame gives 0/0 = NaN as in the reference (quirk Q18).   One warp per frame.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_normalize(const float* __restrict__ V, int n_rows, double* __restrict__ An64, float* __restrict__ An32) {
+k_normalize(const float* __restrict__ V, int n_rows, double* __restrict__ An64, float* __restrict__ An32, int round_tf32) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_rows) return;
     const float* __restrict__ v = V + (size_t)warp * PPITCH;
@@ -31,12 +31,20 @@ k_normalize(const float* __restrict__ V, int n_rows, double* __restrict__ An64, 
     for (int k = lane; k < KPAD; k += 32) {
         const double a = k < NBIN ? (double)v[k] / norm : 0.0;
         if (An64 && k < APITCH64) An64[(size_t)warp * APITCH64 + k] = a;
-        if (An32) An32[(size_t)warp * KPAD + k] = (float)a;
+        if (An32) {
+            float f = (float)a;
+            if (round_tf32) {  // round-to-nearest TF32 here, so the tensor core's operand truncation is exact
+                uint32_t bits;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(f));
+                f = __uint_as_float(bits);
+            }
+            An32[(size_t)warp * KPAD + k] = f;
+        }
     }
 }
 
-void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32) {
-    k_normalize<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(V, n_rows, An64, An32);
+void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, int round_tf32) {
+    k_normalize<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(V, n_rows, An64, An32, round_tf32);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ SIGNATURES = {
     "repet_adaptive_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
     "repet_adaptivemask": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp]),
     "repet_beatspectrogram": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "repet_selfsimilarity": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
     "repet_periods": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "repet_sim_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_sim_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
@@ -583,3 +584,13 @@ def simonline_f64(audio_signal, sampling_frequency, tunables, handle=None, retur
     if return_indices:
         return background, unpack_lists(ints, frames["T"], number)
     return background
+
+
+def selfsimilarity(data_matrix, handle=None):
+    """_selfsimilaritymatrix (repet.py:1209-1225), the device's fast pass: (F, T) -> float32 (T, T)."""
+    handle = handle or get_handle()
+    magnitude = np.ascontiguousarray(np.asarray(data_matrix).T, dtype=np.float32)
+    number_times, number_rows = magnitude.shape
+    out = np.empty((number_times, number_times), dtype=np.float32)
+    handle.check(handle.lib.repet_selfsimilarity(handle.h, _ptr(magnitude), number_times, number_rows, _ptr(out)))
+    return out

@@ -38,6 +38,39 @@ def _assert_lists(lists, counts_ref, flat_ref, what, first=0):
     assert np.array_equal(flat, flat_ref), "%s: %d of %d indices differ" % (what, int(np.sum(flat != flat_ref)), len(flat_ref))
 
 
+@pytest.mark.parametrize("seconds,tensor_core", [(3.0, 1), (13.7, 1), (13.7, 0), (31.0, 1)])
+def test_selfsimilarity_fast_pass(repet, seconds, tensor_core):
+    """The tcgen05 TF32 product (and the fp32 cross-check kernel) against the float64 reference
+    formula: within the bound `tau` the drivers certify against (1.5e-3 / 1e-4)."""
+    x = repet_synth.make_clip(31, int(seconds * FS)).astype(np.float64)
+    N, w, H = oracle.stft_parameters(FS)
+    V = np.mean(np.stack([np.abs(oracle.stft(x[c], w, H)[: N // 2 + 1]) for c in range(2)], axis=2), axis=2)
+    S_ref = oracle.selfsimilaritymatrix(V)
+    repet._host.set_tuning(simgemm_tc=tensor_core)
+    try:
+        S = repet._host.selfsimilarity(V)
+    finally:
+        repet._host.set_tuning(simgemm_tc=1)
+    assert S.shape == S_ref.shape
+    err = float(np.max(np.abs(S - S_ref)))
+    assert err <= (1.5e-3 if tensor_core else 1e-4), err
+    assert np.array_equal(S, S.T)  # both passes are bitwise symmetric
+
+
+def test_sim_lists_do_not_depend_on_the_fast_pass(repet):
+    """TF32 tensor-core pass and fp32 CUDA-core pass propose different candidates; after float64
+    certification the lists must be identical."""
+    x = make_golden.case_input(make_golden.DRIVER_CASES["synth_12s"])
+    y_tc, lists_tc = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    repet._host.set_tuning(simgemm_tc=0)
+    try:
+        y_simt, lists_simt = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    finally:
+        repet._host.set_tuning(simgemm_tc=1)
+    assert all(np.array_equal(a, b) for a, b in zip(lists_tc, lists_simt))
+    assert np.array_equal(y_tc, y_simt)
+
+
 @pytest.mark.parametrize("case", ["wav_5s", "synth_12s", "synth_mono_8s", "wav_full"])
 def test_sim_matches_reference(repet, case, golden_drivers, wav_pcm):
     warnings.simplefilter("ignore")
