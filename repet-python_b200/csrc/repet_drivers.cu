@@ -4,6 +4,8 @@
 #include "repet_internal.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 
 using namespace repet;
@@ -276,7 +278,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         int32_t* idx = bump.take<int32_t>((size_t)g * T * plan.number);
         int32_t* cnt = bump.take<int32_t>((size_t)g * T);
         float* model = bump.take<float>((size_t)g * nch * T * PPITCH);
-        int32_t* overflow = bump.take<int32_t>(1);
+        int32_t* overflow = bump.take<int32_t>(4);  // [overflow flag, candidates, uncertain, neighbour dots]
         float* An32 = online ? nullptr : bump.take<float>((size_t)g * T * KPAD);
         float* S = online ? nullptr : bump.take<float>((size_t)g * T * T);
         Geom geom = clip_geom(g, nch, plan.S, T);
@@ -309,7 +311,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
                     launch_selfsim_simt(st, An32, g, T, S);
                 }
             }
-            CU(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+            CU(cudaMemsetAsync(overflow, 0, 4 * sizeof(int32_t), st));
             Timed timed(h, REPET_K_TOPK);
             if (launch_topk(st, S, An64, g, T, g_tuning.simgemm_tc ? TAU_TF32_GEMM : TAU_FP32_GEMM, plan.p.similarity_threshold, plan.distance, plan.number,
                             idx, cnt, overflow))
@@ -327,10 +329,13 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         int rc = scatter_lists(h, plan, g, idx, cnt, ints + (size_t)clip0 * plan.ints_per_clip);
         if (rc) return rc;
         if (!online) {
-            int32_t flag = 0;
-            CU(cudaMemcpyAsync(&flag, overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            int32_t flag[4] = {0, 0, 0, 0};
+            CU(cudaMemcpyAsync(flag, overflow, sizeof(flag), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            if (flag) return fail(h, REPET_E_UNSUPPORTED, "too many near-tied similarity candidates in one column");
+            if (getenv("REPET_DEBUG_TOPK"))
+                fprintf(stderr, "k_topk: %d columns, %d candidates, %d uncertain, %d near-tie neighbour dots\n", g * T,
+                        flag[1], flag[2], flag[3]);
+            if (flag[0]) return fail(h, REPET_E_UNSUPPORTED, "too many near-tied similarity candidates in one column");
         }
     }
     CU(cudaGetLastError());

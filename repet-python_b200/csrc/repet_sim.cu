@@ -6,6 +6,8 @@
 #include "fft2048.cuh"
 #include "median_networks.cuh"
 
+#include <algorithm>
+
 namespace repet {
 
 // ------------------------------------------------------------------------------------------
@@ -127,18 +129,21 @@ __device__ __forceinline__ double warp_dot64(const double* __restrict__ a, const
 // With tau = 0 this is the reference's rule verbatim (strict >, windows clipped at the ends,
 // NaN never a maximum: quirk Q7).
 // ------------------------------------------------------------------------------------------
-struct TopkSmem {
-    // dynamic layout: float v[T]; double col[APITCH64]; int cand[cap]; double exact[cap]; int flags...
-};
+constexpr int TOPK_THREADS = 512;
+constexpr int TOPK_CAP = 4096;       // candidates per column held in shared memory
+constexpr int TOPK_CHUNK = 8192;     // elements of the fast row resident at a time (3 arrays)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TOPK_THREADS)
 k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, float tau, double thr, int d, int number,
-       int cap, int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ overflow) {
+       int nb, int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* s_col = reinterpret_cast<double*>(smem);                 // [APITCH64]
-    double* s_exact = s_col + APITCH64;                              // [cap]
-    float* s_v = reinterpret_cast<float*>(s_exact + cap);            // [T]
-    int* s_cand = reinterpret_cast<int*>(s_v + ((T + 3) & ~3));      // [cap]  index | uncertain << 30
+    double* s_col = reinterpret_cast<double*>(smem);           // [APITCH64]   column c, float64
+    double* s_exact = s_col + APITCH64;                        // [TOPK_CAP]   exact similarity of candidates
+    int* s_cand = reinterpret_cast<int*>(s_exact + TOPK_CAP);  // [TOPK_CAP]   index | uncertain << 30
+    float* s_vc = reinterpret_cast<float*>(s_cand + TOPK_CAP); // [TOPK_CAP]   fast value of candidates
+    float* s_e = s_vc + TOPK_CAP;                              // [nb*d]       extended chunk of the fast row
+    float* s_pm = s_e + TOPK_CHUNK;                            // prefix maxima within blocks of d
+    float* s_sm = s_pm + TOPK_CHUNK;                           // suffix maxima within blocks of d
     __shared__ int s_count, s_kept;
     const int item = blockIdx.y, c = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
@@ -148,45 +153,73 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
         s_count = 0;
         s_kept = 0;
     }
-    for (int i = t; i < T; i += blockDim.x) s_v[i] = row[i];
     for (int k = t; k < APITCH64; k += blockDim.x) s_col[k] = A[(size_t)c * APITCH64 + k];
-    __syncthreads();
     const float thr_f = (float)thr;
-    // ---- propose -----------------------------------------------------------------------------
-    for (int i = t; i < T; i += blockDim.x) {
-        const float v = s_v[i];
-        if (!(v >= thr_f - tau)) continue;  // also drops NaN
-        bool dropped = false, uncertain = !(v >= thr_f + tau);
-        const int lo = max(i - d, 0), hi = min(i + d, T - 1);
-        for (int off = 1; off <= d && !dropped; ++off) {
-            const int ul = i - off, ur = i + off;
-            if (ul >= lo) {
-                const float w = s_v[ul];
-                if (!(w < v + 2.f * tau)) dropped = true;  // w >= v + 2 tau, or NaN
-                else if (w > v - 2.f * tau) uncertain = true;
+    const float two_tau = 2.f * tau;
+    // ---- propose: sliding-window maxima by van Herk / Gil-Werman on chunks of the row -----------
+    // chunk = nb blocks of d elements: one halo block on each side, nb-2 payload blocks
+    const int payload = d > 0 ? (nb - 2) * d : TOPK_CHUNK;
+    for (int g0 = 0; g0 < T; g0 += payload) {
+        __syncthreads();
+        if (d > 0) {
+            const int ext = nb * d;
+            for (int x = t; x < ext; x += blockDim.x) {
+                const int g = g0 - d + x;
+                float v = (g >= 0 && g < T) ? row[g] : -INFINITY;
+                if (v != v) v = INFINITY;  // NaN is never a maximum and blocks its neighbours (quirk Q7)
+                s_e[x] = v;
             }
-            if (ur <= hi) {
-                const float w = s_v[ur];
-                if (!(w < v + 2.f * tau)) dropped = true;
-                else if (w > v - 2.f * tau) uncertain = true;
+            __syncthreads();
+            for (int blk = t; blk < nb; blk += blockDim.x) {
+                float m = -INFINITY;
+                for (int x = blk * d; x < (blk + 1) * d; ++x) {
+                    m = fmaxf(m, s_e[x]);
+                    s_pm[x] = m;
+                }
+                m = -INFINITY;
+                for (int x = (blk + 1) * d - 1; x >= blk * d; --x) {
+                    m = fmaxf(m, s_e[x]);
+                    s_sm[x] = m;
+                }
             }
+            __syncthreads();
+        } else {
+            for (int x = t; x < payload; x += blockDim.x) {
+                const int g = g0 + x;
+                float v = g < T ? row[g] : -INFINITY;
+                if (v != v) v = INFINITY;
+                s_e[x] = v;
+            }
+            __syncthreads();
         }
-        if (tau == 0.f) {
-            // exact fast values: ties (w == v) are decided right here by the strict rule
-            // (handled above: w >= v drops), nothing is uncertain
-            uncertain = false;
-        }
-        if (!dropped) {
+        for (int x = t; x < payload; x += blockDim.x) {
+            const int i = g0 + x;
+            if (i >= T) break;
+            const int xe = d > 0 ? x + d : x;
+            const float v = s_e[xe];
+            if (!(v >= thr_f - tau) || !(v < INFINITY)) continue;
+            float m = -INFINITY;
+            if (d > 0) {
+                // left window [xe-d, xe-1] and right window [xe+1, xe+d]: each exactly one block long
+                m = fmaxf(fmaxf(s_sm[xe - d], s_pm[xe - 1]), fmaxf(s_sm[xe + 1], s_pm[xe + d]));
+            }
+            if (!(m < v + two_tau)) continue;  // a neighbour is at least 2 tau above (or is NaN): not a maximum
+            if (tau == 0.f && !(m < v)) continue;  // exact fast values: the strict rule decides ties here
+            const bool uncertain = tau > 0.f && ((m > v - two_tau) || !(v >= thr_f + tau));
             const int slot = atomicAdd(&s_count, 1);
-            if (slot < cap) s_cand[slot] = i | (uncertain ? (1 << 30) : 0);
+            if (slot < TOPK_CAP) {
+                s_cand[slot] = i | (uncertain ? (1 << 30) : 0);
+                s_vc[slot] = v;
+            }
         }
     }
     __syncthreads();
     int count = s_count;
-    if (count > cap) {
+    if (count > TOPK_CAP) {
         if (t == 0) atomicExch(overflow, 1);
-        count = cap;
+        count = TOPK_CAP;
     }
+    if (t == 0) atomicAdd(overflow + 1, count);  // statistics: candidates proposed
     // ---- exact values of every candidate -------------------------------------------------------
     for (int q = warp; q < count; q += nwarp) {
         const int i = s_cand[q] & 0x3fffffff;
@@ -200,17 +233,19 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
         if (!(code & (1 << 30))) continue;
         const int i = code & 0x3fffffff;
         const double e = s_exact[q];
-        const float v = s_v[i];
+        const float v = s_vc[q];
         bool keep = e >= thr;
+        if (lane == 0) atomicAdd(overflow + 2, 1);  // statistics: uncertain candidates
         const int lo = max(i - d, 0), hi = min(i + d, T - 1);
         for (int u0 = lo; u0 <= hi && keep; u0 += 32) {
             const int u = u0 + lane;
-            const bool near_tie = u <= hi && u != i && (s_v[u] > v - 2.f * tau);
+            const bool near_tie = u <= hi && u != i && (row[u] > v - two_tau);
             unsigned mask = __ballot_sync(0xffffffffu, near_tie);
             while (mask && keep) {
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const double eu = warp_dot64(s_col, A + (size_t)(u0 + src) * APITCH64, lane);
+                if (lane == 0) atomicAdd(overflow + 3, 1);  // statistics: near-tie neighbour dots
                 if (!(e > eu)) keep = false;  // strict >, NaN never passes
             }
         }
@@ -238,29 +273,22 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     if (t == 0) cnt_out[(size_t)item * T + c] = min(s_kept, number);
 }
 
-size_t topk_smem_bytes(int T, int cap) {
-    return (size_t)APITCH64 * 8 + (size_t)cap * 8 + (size_t)((T + 3) & ~3) * 4 + (size_t)cap * 4;
-}
-
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
                 int number, int* idx_out, int* cnt_out, int* overflow) {
-    int cap = T;
-    size_t smem = topk_smem_bytes(T, cap);
-    const size_t limit = 220 * 1024;
-    if (smem > limit) {
-        // keep the fast row resident, give the rest to candidates
-        const size_t fixed = (size_t)APITCH64 * 8 + (size_t)((T + 3) & ~3) * 4;
-        if (fixed + 12 * 256 > limit) return -1;  // row does not fit: the caller reports UNSUPPORTED
-        cap = (int)((limit - fixed) / 12);
-        smem = topk_smem_bytes(T, cap);
+    // blocks of d elements per chunk: as many as fit, at least halo + one payload block
+    int nb = 3;
+    if (d > 0) {
+        nb = std::min(TOPK_THREADS, TOPK_CHUNK / d);
+        if (nb < 3) return -1;  // similarity_distance too large for the shared-memory window
     }
-    static size_t configured = 0;
-    if (smem > configured) {
+    const size_t smem = (size_t)APITCH64 * 8 + (size_t)TOPK_CAP * 16 + 3 * (size_t)TOPK_CHUNK * 4;
+    static bool configured = false;
+    if (!configured) {
         cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+        configured = true;
     }
     dim3 grid(T, n_items);
-    k_topk<<<grid, 256, smem, st>>>(S, An64, T, tau, thr, d, number, cap, idx_out, cnt_out, overflow);
+    k_topk<<<grid, TOPK_THREADS, smem, st>>>(S, An64, T, tau, thr, d, number, nb, idx_out, cnt_out, overflow);
     return 0;
 }
 
@@ -337,7 +365,7 @@ void launch_online_select(cudaStream_t st, const double* An64, int n_items, int 
 // model[j][c][bin] = median over u in list(j) of |X_c[u][bin]| (an empty list gives NaN, as
 // np.median of an empty selection does).  One CTA per (frame, item*channel).  Lists of up to 32
 // frames go through the register selection networks on bin pairs; longer lists are staged as
-// squared magnitudes in shared memory [n][256 bins] and selected by counting ranks.
+// squared magnitudes in shared memory [n][256 bins] and selected by an in-place quickselect.
 // ------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ float2 gather_median_pair(const float2* __restrict__ chan, size_t row, const int* __restrict__ list,
@@ -377,36 +405,46 @@ __device__ __forceinline__ void simmodel_small(const float2* __restrict__ chan, 
     }
 }
 
-// median of column `col` of a [n][pitch] shared-memory tile of squared magnitudes, by rank counting
-__device__ __forceinline__ float tile_median(const float* __restrict__ tile, int n, int pitch, int col) {
-    const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
-    float v_lo = 0.f, v_hi = 0.f;
-    bool got_lo = false, got_hi = false;
-    for (int a = 0; a < n && !(got_lo && got_hi); ++a) {
-        const float va = tile[a * pitch + col];
-        int less = 0, equal = 0;
-        for (int b = 0; b < n; ++b) {
-            const float vb = tile[b * pitch + col];
-            less += vb < va;
-            equal += vb == va;
+// median of column `col` of a [n][pitch] shared-memory tile of squared magnitudes: in-place Hoare
+// quickselect of the upper middle element (expected ~3n compares instead of the n^2 of rank counting),
+// then the lower middle = max of what ended up left of it.  The column is private to the thread.
+__device__ __forceinline__ float tile_median(float* __restrict__ tile, int n, int pitch, int col) {
+    float* __restrict__ v = tile + col;
+    const int k = n >> 1;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const float a = v[lo * pitch], b = v[((lo + hi) >> 1) * pitch], c = v[hi * pitch];
+        const float pivot = fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));  // median of three
+        int i = lo, j = hi;
+        while (i <= j) {
+            while (v[i * pitch] < pivot) ++i;
+            while (v[j * pitch] > pivot) --j;
+            if (i <= j) {
+                const float x = v[i * pitch];
+                v[i * pitch] = v[j * pitch];
+                v[j * pitch] = x;
+                ++i;
+                --j;
+            }
         }
-        if (!got_lo && less <= k_lo && k_lo < less + equal) {
-            v_lo = va;
-            got_lo = true;
-        }
-        if (!got_hi && less <= k_hi && k_hi < less + equal) {
-            v_hi = va;
-            got_hi = true;
-        }
+        if (k <= j) hi = j;
+        else if (k >= i) lo = i;
+        else break;
     }
+    const float v_hi = v[k * pitch];
+    if (n & 1) return fast_sqrt(v_hi);
+    float v_lo = -INFINITY;
+    for (int s = 0; s < k; ++s) v_lo = fmaxf(v_lo, v[s * pitch]);
     return 0.5f * (fast_sqrt(v_lo) + fast_sqrt(v_hi));
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int SIMMODEL_THREADS = 256;
+
+__global__ void __launch_bounds__(SIMMODEL_THREADS)
 k_simmodel(const float2* __restrict__ X, int T, int nch, const int* __restrict__ idx, const int* __restrict__ cnt,
            int number, int first_frame, float* __restrict__ model) {
     extern __shared__ __align__(16) unsigned char smem[];
-    int* s_list = reinterpret_cast<int*>(smem);                       // [number]
+    int* s_list = reinterpret_cast<int*>(smem);                              // [number]
     float* s_tile = reinterpret_cast<float*>(s_list + ((number + 3) & ~3));  // [n][256] when n > 32
     const int j = blockIdx.x + first_frame;
     const int item = blockIdx.y / nch, c = blockIdx.y - item * nch;
@@ -415,40 +453,51 @@ k_simmodel(const float2* __restrict__ X, int T, int nch, const int* __restrict__
     const float2* __restrict__ chan = X + (size_t)item * T * row + (size_t)c * XPITCH;
     float* __restrict__ out = model + (((size_t)item * nch + c) * (size_t)T + j) * PPITCH;
     const int n = cnt[(size_t)item * T + j];
-    for (int s = t; s < n; s += 128) s_list[s] = idx[((size_t)item * T + j) * (size_t)number + s];
+    for (int s = t; s < n; s += SIMMODEL_THREADS) s_list[s] = idx[((size_t)item * T + j) * (size_t)number + s];
     __syncthreads();
-    switch (n) {
-        case 0:
-            for (int k = t; k <= XPITCH; k += 128) out[k] = nanf("");
-            break;
+    if (n == 0) {
+        for (int k = t; k <= XPITCH; k += SIMMODEL_THREADS) out[k] = nanf("");
+        return;
+    }
+    if (n <= 32) {
+        // short lists: register selection networks on bin pairs, 128 threads x 4 passes
+        if (t < 128) {
+            switch (n) {
 #define REPET_CASE(N) case N: simmodel_small<N>(chan, row, s_list, out, t); break;
-            REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
-            REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
-            REPET_CASE(15) REPET_CASE(16) REPET_CASE(17) REPET_CASE(18) REPET_CASE(19) REPET_CASE(20) REPET_CASE(21)
-            REPET_CASE(22) REPET_CASE(23) REPET_CASE(24) REPET_CASE(25) REPET_CASE(26) REPET_CASE(27) REPET_CASE(28)
-            REPET_CASE(29) REPET_CASE(30) REPET_CASE(31) REPET_CASE(32)
+                REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+                REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+                REPET_CASE(15) REPET_CASE(16) REPET_CASE(17) REPET_CASE(18) REPET_CASE(19) REPET_CASE(20) REPET_CASE(21)
+                REPET_CASE(22) REPET_CASE(23) REPET_CASE(24) REPET_CASE(25) REPET_CASE(26) REPET_CASE(27) REPET_CASE(28)
+                REPET_CASE(29) REPET_CASE(30) REPET_CASE(31) REPET_CASE(32)
 #undef REPET_CASE
-        default: {
-            // long lists: stage squared magnitudes [n][256 bins] per pass, then count ranks
-            for (int pass = 0; pass < 4; ++pass) {
-                const int k = 2 * t + 256 * pass;
-                for (int s = 0; s < n; ++s) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(chan + (size_t)s_list[s] * row + k));
-                    s_tile[s * 256 + 2 * t] = (k == 0) ? __fmul_rn(x.x, x.x) : __fmaf_rn(x.x, x.x, __fmul_rn(x.y, x.y));
-                    s_tile[s * 256 + 2 * t + 1] = __fmaf_rn(x.z, x.z, __fmul_rn(x.w, x.w));
-                }
-                // each thread reads back only what it wrote: no barrier needed
-                out[k] = tile_median(s_tile, n, 256, 2 * t);
-                out[k + 1] = tile_median(s_tile, n, 256, 2 * t + 1);
-            }
-            if (t == 0) {
-                for (int s = 0; s < n; ++s) {
-                    const float y = __ldg(&chan[(size_t)s_list[s] * row]).y;
-                    s_tile[s * 256] = __fmul_rn(y, y);
-                }
-                out[XPITCH] = tile_median(s_tile, n, 256, 0);
             }
         }
+        return;
+    }
+    // long lists: one bin per thread, 4 passes of 256 bins; squared magnitudes staged in the thread's
+    // own shared-memory column (bank = lane: conflict free), 8 gathers in flight per thread
+    for (int pass = 0; pass < 4; ++pass) {
+        const int k = t + 256 * pass;
+        for (int s0 = 0; s0 < n; s0 += 8) {
+            float2 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ldg(chan + (size_t)s_list[min(s0 + u, n - 1)] * row + k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s = s0 + u;
+                if (s < n)
+                    s_tile[s * 256 + t] = (k == 0) ? __fmul_rn(x[u].x, x[u].x) : __fmaf_rn(x[u].x, x[u].x, __fmul_rn(x[u].y, x[u].y));
+            }
+        }
+        out[k] = tile_median(s_tile, n, 256, t);  // the column is private: no barrier needed
+    }
+    if (t == 0) {
+        // Nyquist rides in bin 0's imaginary slot
+        for (int s = 0; s < n; ++s) {
+            const float y = __ldg(&chan[(size_t)s_list[s] * row]).y;
+            s_tile[s * 256] = __fmul_rn(y, y);
+        }
+        out[XPITCH] = tile_median(s_tile, n, 256, 0);
     }
 }
 
@@ -463,7 +512,7 @@ int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nc
     }
     if (T <= first_frame) return 0;
     dim3 grid(T - first_frame, n_items * nch);
-    k_simmodel<<<grid, 128, smem, st>>>(X, T, nch, idx, cnt, number, first_frame, model);
+    k_simmodel<<<grid, SIMMODEL_THREADS, smem, st>>>(X, T, nch, idx, cnt, number, first_frame, model);
     return 0;
 }
 
