@@ -292,7 +292,7 @@ static int beat_common(repet_handle* h, const float* spectrogram, int n_frames, 
     CU(cudaMemcpy2DAsync(P, PPITCH * sizeof(float), spectrogram, n_rows * sizeof(float), n_rows * sizeof(float),
                          n_frames, cudaMemcpyHostToDevice, st));
     launch_beat(st, P, 1, n_frames, 0, n_frames, 0, 1, tables(h), psd, n_parts, f_per_part);
-    launch_periods(st, psd, 1, n_parts, n_frames, (double)n_rows, lag_lo, lag_hi, 0, beat ? n_frames : 0,
+    launch_periods(st, psd, nullptr, 1, n_parts, n_frames, (double)n_rows, lag_lo, lag_hi, 0, beat ? n_frames : 0,
                    beat ? b : nullptr, BEAT_L, period ? per : nullptr, nullptr);
     h->launches += 2;
     if (beat) CU(cudaMemcpyAsync(beat, b, (size_t)n_frames * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -414,7 +414,7 @@ int repet_beatspectrogram(repet_handle* h, const float* spectrogram, int n_frame
                          cudaMemcpyHostToDevice, st));
     const int left = segment_length / 2;  // ceil((L-1)/2), repet.py:1182
     launch_beat(st, P, 1, n_frames, -left, segment_length, segment_step, n_seg, tables(h), psd, n_parts, f_per_part);
-    launch_periods(st, psd, n_seg, n_parts, segment_length, (double)n_rows, 0, 0, 0, segment_length, b, segment_length,
+    launch_periods(st, psd, nullptr, n_seg, n_parts, segment_length, (double)n_rows, 0, 0, 0, segment_length, b, segment_length,
                    nullptr, nullptr);
     h->launches += 2;
     CU(cudaMemcpyAsync(beat, b, (size_t)n_seg * segment_length * sizeof(double), cudaMemcpyDeviceToHost, st));

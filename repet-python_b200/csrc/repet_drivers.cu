@@ -27,6 +27,8 @@ constexpr float TAU_TF32_GEMM = 1.5e-3f;
 // ---------------------------------------------------------------------------------------------
 struct PeriodShape {
     int T = 0, lag_hi = 0, pmax = 0, n_parts = 0, f_per_part = 0;
+    // clips longer than one beat transform: blocks of `block_frames` frames, complex partials
+    int n_blocks = 1, block_frames = 0;
     size_t bytes_per_item = 0;
 };
 
@@ -44,16 +46,22 @@ int period_shape(repet_handle* h, const repet_params* p, int nch, int64_t n_samp
     if (p->period_lo < 0 || lag_hi <= p->period_lo)
         return fail(h, REPET_E_TOO_SHORT,
                     "attempt to get argmax of an empty sequence (signal too short for the period range)");
-    if (T + lag_hi - 1 > BEAT_L)
-        return fail(h, REPET_E_UNSUPPORTED, "clip longer than the single-block beat transform (T + max lag > 2048 frames)");
     s->T = T;
     s->lag_hi = lag_hi;
     s->pmax = lag_hi;  // period = lag + 1 <= lag_hi
-    pick_beat_parts(h, chunk_hint, 64, &s->n_parts, &s->f_per_part);
+    s->n_blocks = 1;
+    s->block_frames = 0;
+    if (T + lag_hi - 1 > BEAT_L) {
+        if (lag_hi > BEAT_L / 2)
+            return fail(h, REPET_E_UNSUPPORTED, "period range above 1024 frames needs a longer beat transform");
+        s->block_frames = BEAT_L - lag_hi + 1;
+        s->n_blocks = (T + s->block_frames - 1) / s->block_frames;
+    }
+    pick_beat_parts(h, chunk_hint * s->n_blocks, s->n_blocks > 1 ? 16 : 64, &s->n_parts, &s->f_per_part);
     size_t b = 0;
     b += align_up((size_t)T * nch * XPITCH * sizeof(float2));
     b += align_up((size_t)T * PPITCH * sizeof(float));
-    b += align_up((size_t)s->n_parts * BEAT_L * sizeof(float));
+    b += (s->n_blocks > 1 ? 2 : 1) * align_up((size_t)s->n_blocks * s->n_parts * BEAT_L * sizeof(float));
     b += align_up((size_t)nch * s->pmax * PPITCH * sizeof(float));
     b += 512;
     s->bytes_per_item = b;
@@ -80,7 +88,10 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
         Bump bump(ws);
         float2* X = bump.take<float2>((size_t)g_items * s.T * nch * XPITCH);
         float* P = bump.take<float>((size_t)g_items * s.T * PPITCH);
-        float* psd = bump.take<float>((size_t)g_items * s.n_parts * BEAT_L);
+        const bool blocked = s.n_blocks > 1;
+        const int total_parts = s.n_blocks * s.n_parts;
+        float* psd = bump.take<float>((size_t)g_items * total_parts * BEAT_L);
+        float* psd_im = blocked ? bump.take<float>((size_t)g_items * total_parts * BEAT_L) : nullptr;
         float* model = bump.take<float>((size_t)g_items * nch * s.pmax * PPITCH);
         gin.n_items = gout.n_items = g_items;
         gin.item0 = gout.item0 = first;
@@ -91,12 +102,16 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
         }
         {
             Timed timed(h, REPET_K_BEAT);
-            launch_beat(st, P, g_items, s.T, 0, s.T, 0, 1, tables(h), psd, s.n_parts, s.f_per_part);
+            if (blocked)
+                launch_beat_blocked(st, P, g_items, s.T, s.block_frames, s.lag_hi, tables(h), psd, psd_im, s.n_blocks,
+                                    s.n_parts, s.f_per_part);
+            else
+                launch_beat(st, P, g_items, s.T, 0, s.T, 0, 1, tables(h), psd, s.n_parts, s.f_per_part);
         }
         {
             Timed timed(h, REPET_K_PERIODS);
-            launch_periods(st, psd, g_items, s.n_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr, 0,
-                           periods_dev + first, nullptr);
+            launch_periods(st, psd, psd_im, g_items, total_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr,
+                           0, periods_dev + first, nullptr);
         }
         {
             Timed timed(h, REPET_K_MODEL);
@@ -419,7 +434,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         }
         {
             Timed timed(h, REPET_K_PERIODS);
-            launch_periods(st, psd, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
+            launch_periods(st, psd, nullptr, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
                            plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr);
         }
         {

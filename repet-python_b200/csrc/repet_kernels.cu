@@ -240,12 +240,14 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
 // of the argmax.  period = first argmax over lags [lo, hi) + 1 (quirks Q1, Q2).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double norm_rows, int lag_lo, int lag_hi,
-          int out_lo, int out_hi, double* __restrict__ beat_out, int beat_pitch, int* __restrict__ period,
-          double* __restrict__ stats) {
-    __shared__ double s_psd[BEAT_L / 2 + 1];
-    __shared__ double s_cos[BEAT_L];
-    __shared__ double s_b[BEAT_L];
+k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part_im, int n_parts, int t_len,
+          double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* __restrict__ beat_out,
+          int beat_pitch, int* __restrict__ period, double* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char s_raw_periods[];
+    double* s_cos = reinterpret_cast<double*>(s_raw_periods);  // [BEAT_L]      cos(2 pi k / L)
+    double* s_b = s_cos + BEAT_L;                              // [BEAT_L]      partial sums, then b[l]
+    double* s_psd = s_b + BEAT_L;                              // [BEAT_L/2+1]  symmetric part of Re G
+    double* s_im = s_psd + BEAT_L / 2 + 1;                     // [BEAT_L/2+1]  antisymmetric part of Im G
     const int t = threadIdx.x;
     const int bi = blockIdx.x;
     for (int k = t; k < BEAT_L; k += 256) {
@@ -258,6 +260,18 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
     __syncthreads();
     for (int k = t; k <= BEAT_L / 2; k += 256) s_psd[k] = 0.5 * (s_b[k] + s_b[(BEAT_L - k) & (BEAT_L - 1)]);
     __syncthreads();
+    if (psd_part_im) {
+        // blocked cross-spectrum G = sum conj(A) C: r[l] = (1/L) sum_k Re G cos - Im G sin, G Hermitian
+        for (int k = t; k < BEAT_L; k += 256) {
+            double a = 0.0;
+            const float* __restrict__ src = psd_part_im + (size_t)bi * n_parts * BEAT_L + k;
+            for (int part = 0; part < n_parts; ++part) a += (double)src[(size_t)part * BEAT_L];
+            s_b[k] = a;
+        }
+        __syncthreads();
+        for (int k = t; k <= BEAT_L / 2; k += 256) s_im[k] = 0.5 * (s_b[k] - s_b[(BEAT_L - k) & (BEAT_L - 1)]);
+        __syncthreads();
+    }
     int l0 = out_lo, l1 = out_hi;
     if (period) {
         l0 = (out_hi > out_lo) ? min(out_lo, lag_lo) : lag_lo;
@@ -265,7 +279,15 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
     }
     for (int l = l0 + t; l < l1; l += 256) {
         double s = 0.0;
-        for (int k = 1; k < BEAT_L / 2; ++k) s = fma(s_psd[k], s_cos[(k * l) & (BEAT_L - 1)], s);
+        if (psd_part_im) {
+            for (int k = 1; k < BEAT_L / 2; ++k) {
+                const int ph = (k * l) & (BEAT_L - 1);
+                s = fma(s_psd[k], s_cos[ph], s);
+                s = fma(-s_im[k], s_cos[(ph - BEAT_L / 4) & (BEAT_L - 1)], s);  // sin(x) = cos(x - pi/2)
+            }
+        } else {
+            for (int k = 1; k < BEAT_L / 2; ++k) s = fma(s_psd[k], s_cos[(k * l) & (BEAT_L - 1)], s);
+        }
         s = 2.0 * s + s_psd[0] + ((l & 1) ? -s_psd[BEAT_L / 2] : s_psd[BEAT_L / 2]);
         s_b[l] = s / (double)BEAT_L / ((double)(t_len - l) * norm_rows);
     }
@@ -297,11 +319,126 @@ k_periods(const float* __restrict__ psd_part, int n_parts, int t_len, double nor
     }
 }
 
-void launch_periods(cudaStream_t st, const float* psd_part, int n_beat_items, int n_parts, int t_len, double norm_rows,
-                    int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out, int beat_pitch, int* period,
-                    double* stats) {
-    k_periods<<<n_beat_items, 256, 0, st>>>(psd_part, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo, out_hi,
-                                            beat_out, beat_pitch, period, stats);
+void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_part_im, int n_beat_items, int n_parts,
+                    int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
+                    int beat_pitch, int* period, double* stats) {
+    const size_t smem = (size_t)(2 * BEAT_L + 2 * (BEAT_L / 2 + 1)) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_periods, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_periods<<<n_beat_items, 256, smem, st>>>(psd_part, psd_part_im, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo,
+                                              out_hi, beat_out, beat_pitch, period, stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_beat_blocked  --  the beat spectrum of clips longer than one transform
+// For T + max lag > 2048 the time axis is cut into blocks of Bk = 2048 - max lag + 1 frames.
+// Block b correlates a = P[b Bk .. b Bk + Bk) with c = P[b Bk .. b Bk + Bk + max lag - 1) (zero past
+// T): sum_t a[t] c[t + l] has no circular alias for l < max lag.  One complex transform of
+// z = a + i c gives A = (Z[k] + conj Z[-k])/2 and C = (Z[k] - conj Z[-k])/(2i); the kernel
+// accumulates the cross-spectrum G[k] = conj(A) C over its rows in registers (thread-owned bins
+// k and -k are paired through shared memory) and k_periods inverts sum G once per clip.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FFT_THREADS)
+k_beat_blocked(const float* __restrict__ P, int T, int Bk, int max_lag, FftTables tb, float* __restrict__ g_re,
+               float* __restrict__ g_im, int n_fparts, int f_per_part, int TP) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float2* s_bufA = reinterpret_cast<float2*>(s_raw);
+    float2* s_bufB = s_bufA + FFT_BUF;
+    float2* s_tw2 = s_bufB + FFT_BUF;
+    float* s_tile = reinterpret_cast<float*>(s_tw2 + 128);  // [8][TP] rows of P, time contiguous
+    const int t = threadIdx.x;
+    const int item = blockIdx.z;
+    const int blk = blockIdx.y;
+    const int fpart = blockIdx.x;
+    const int n_blocks = gridDim.y;
+    const int t0 = blk * Bk;
+    const int span = min(Bk + max_lag - 1, T - t0);  // valid frames of c
+    const int a_len = min(Bk, T - t0);               // valid frames of a
+    const int f_begin = fpart * f_per_part;
+    const int f_end = min(NBIN, f_begin + f_per_part);
+    s_tw2[t] = tb.tw2[t];
+    Twiddle1 tw;
+    tw.load(tb.tw1, t);
+    float acc_re[16], acc_im[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc_re[i] = acc_im[i] = 0.f;
+    const float* __restrict__ Pitem = P + (size_t)item * T * PPITCH;
+    for (int f0 = f_begin; f0 < f_end; f0 += 8) {
+        __syncthreads();
+        for (int idx = t; idx < 2 * span; idx += FFT_THREADS) {
+            const int row = idx >> 1, half = idx & 1;
+            float4 v = __ldg(reinterpret_cast<const float4*>(Pitem + (size_t)(t0 + row) * PPITCH + f0 + 4 * half));
+            const int f = f0 + 4 * half;
+            if (f + 0 >= f_end) v.x = 0.f;
+            if (f + 1 >= f_end) v.y = 0.f;
+            if (f + 2 >= f_end) v.z = 0.f;
+            if (f + 3 >= f_end) v.w = 0.f;
+            s_tile[(4 * half + 0) * TP + row] = v.x;
+            s_tile[(4 * half + 1) * TP + row] = v.y;
+            s_tile[(4 * half + 2) * TP + row] = v.z;
+            s_tile[(4 * half + 3) * TP + row] = v.w;
+        }
+        __syncthreads();
+        const int nrows = min(8, f_end - f0);
+        for (int fr = 0; fr < nrows; ++fr) {
+            float2 r[16];
+            const float* __restrict__ col = s_tile + fr * TP;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const int n = n1 * 128 + t;
+                const float c = n < span ? col[n] : 0.f;
+                r[n1] = make_float2(n < a_len ? c : 0.f, c);
+            }
+            fft_stage1(r, tw, s_bufA, t);
+            __syncthreads();
+            fft_stage2(r, s_bufA, s_bufB, s_tw2, t);
+            __syncthreads();
+            fft_stage3(r, s_bufB, t);
+            // Z in natural order (bufA is free: its readers finished before the last barrier)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k3 = 0; k3 < 8; ++k3) s_bufA[t + 128 * h + 256 * k3] = r[h * 8 + k3];
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = t + 128 * i;
+                const float2 p = s_bufA[k];
+                const float2 zq = s_bufA[(FFT_N - k) & (FFT_N - 1)];
+                const float2 q = make_float2(zq.x, -zq.y);  // conj Z[-k]
+                // conj(A) C = conj(p + q) * (-i) (p - q) / 4
+                const float sx = p.x + q.x, sy = -(p.y + q.y);  // conj(p + q)
+                const float dx = p.y - q.y, dy = -(p.x - q.x);  // -i (p - q)
+                acc_re[i] = fmaf(0.25f, sx * dx - sy * dy, acc_re[i]);
+                acc_im[i] = fmaf(0.25f, sx * dy + sy * dx, acc_im[i]);
+            }
+            // the next row's stage 1 writes bufA: every thread must be done reading it
+            __syncthreads();
+        }
+    }
+    const size_t part = ((size_t)item * n_blocks + blk) * n_fparts + fpart;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        g_re[part * BEAT_L + t + 128 * i] = acc_re[i];
+        g_im[part * BEAT_L + t + 128 * i] = acc_im[i];
+    }
+}
+
+void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, int Bk, int max_lag, FftTables tb,
+                         float* g_re, float* g_im, int n_blocks, int n_fparts, int f_per_part) {
+    const int rows = Bk + max_lag - 1;
+    const int TP = ((rows + 7) / 8) * 8 + 4;
+    const size_t smem = (size_t)(2 * FFT_BUF + 128) * sizeof(float2) + (size_t)8 * TP * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_beat_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid(n_fparts, n_blocks, n_items);
+    k_beat_blocked<<<grid, FFT_THREADS, smem, st>>>(P, T, Bk, max_lag, tb, g_re, g_im, n_fparts, f_per_part, TP);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -62,9 +62,13 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
                  FftTables tb, float* psd_part, int n_parts, int f_per_part);
 
 // k_periods: partial PSDs -> beat spectrum b[l] (optional) and argmax period per beat item (fp64)
-void launch_periods(cudaStream_t st, const float* psd_part, int n_beat_items, int n_parts, int t_len, double norm_rows,
-                    int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out, int beat_pitch, int* period,
-                    double* stats);
+void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_part_im, int n_beat_items, int n_parts,
+                    int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
+                    int beat_pitch, int* period, double* stats);
+// k_beat_blocked: clips longer than one transform, complex cross-spectrum partials
+// g_re / g_im [item][block][fpart][2048]
+void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, int Bk, int max_lag, FftTables tb,
+                         float* g_re, float* g_im, int n_blocks, int n_fparts, int f_per_part);
 
 // k_model: median over the period-strided frames of every phase -> model[item][c][q][PPITCH]
 void launch_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,

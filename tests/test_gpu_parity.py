@@ -265,3 +265,24 @@ def test_full_size_clip_properties(repet):
     swapped, periods_swapped = repet.original_batch(np.ascontiguousarray(audio[:, ::-1, :]), FS)
     assert np.array_equal(periods_swapped, periods)
     assert _rel(swapped[:, ::-1, :], background) <= 1e-5
+
+
+def test_original_long_clip_blocked_beat_transform(repet):
+    """Clips longer than one 2048-point beat transform (T + max lag > 2048 frames, i.e. > ~37 s)
+    take the blocked cross-spectrum path; medians over more than 32 segments take the
+    rank-selection path.  90 s of audio: T = 3877."""
+    x = repet_synth.make_clip(77, 90 * FS).T.astype(np.float64)
+    y, period = repet._host.original_f64(x, FS, repet._tunables(), return_period=True)
+    y_ref, det = oracle.original(x, FS, return_details=True)
+    assert period == det["period"]
+    _assert_signal(y, y_ref, "original, 90 s")
+    # a short period range makes ceil(T / p) > 32
+    saved = repet.period_range
+    try:
+        repet.period_range = [0.5, 2]
+        y2, period2 = repet._host.original_f64(x, FS, repet._tunables(), return_period=True)
+    finally:
+        repet.period_range = saved
+    y2_ref, det2 = oracle.original(x, FS, return_details=True, period_range=(0.5, 2))
+    assert period2 == det2["period"] and -(-3877 // period2) > 32
+    _assert_signal(y2, y2_ref, "original, 90 s, short periods")
