@@ -8,15 +8,15 @@
 // Decomposition (Cooley-Tukey, n = n1*128 + n2*8 + m2, k = k1 + 16*k2 + 256*k3):
 //   stage 1  thread m = t            : DFT-16 over n1 of x[n1*128 + m], times W_2048^(m*k1)
 //   stage 2  thread (k1 = t%16, m2 = t/16): DFT-16 over n2 of y1[k1][n2*8 + m2], times W_128^(m2*k2)
-//   stage 3  thread pi in {t, t+128} (k1 = pi%16, k2 = pi/16): DFT-8 over m2 of y2[k2][m2][k1]
+//   stage 3  thread owns columns pi in {t, 256-t} (k1 = pi%16, k2 = pi/16): DFT-8 over m2 of y2[k2][m2][k1]
 //            -> Z[pi + 256*k3]
 // The two exchanges go through shared memory with layouts chosen so that every access of
 // a half-warp (8-byte elements) is bank-conflict free:
 //   y1 at [k1*129 + m]           (row pad 1: stage-2 reads have stride 129 float2 = 258 words)
 //   y2 at [(k2*8 + m2)*16 + k1]  (k1 fastest: stage-2 writes and stage-3 reads are contiguous)
 // A thread owns the same residues mod 128 on input (n1*128 + t) and, mod 256, on output
-// (pi + 256*k3), which lets the STFT keep the overlapping half frame and the ISTFT do its
-// overlap-add entirely in registers.
+// (columns t and 256 - t, see fft_out_column), which lets the STFT keep the overlapping half
+// frame, split the two packed channels, and the ISTFT do its overlap-add, all in registers.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -134,11 +134,18 @@ __device__ __forceinline__ void fft_stage2(float2 (&r)[16], const float2* __rest
     for (int k2 = 1; k2 < 16; ++k2) dst[(k2 * 8 + m2) * 16 + k1] = cmul(r[k2], s_tw2[k2 * 8 + m2]);
 }
 
-// stage 3: reads y2 from src; on exit r[h*8 + k3] = Z[(t + 128*h) + 256*k3].
+// The two output columns (residues mod 256) a thread owns after stage 3: t and 256 - t, except
+// thread 0 which owns the two self-mirrored columns 0 and 128.  Column c and column 256 - c hold
+// each other's mirror bins (2048 - (c + 256 k3) = (256 - c) + 256 (7 - k3)), so a thread has
+// Z[k] AND Z[2048 - k] in registers: the Hermitian split of two packed real channels needs no
+// further exchange.  Time-domain use: samples n and n + 1024 sit in the same column (k3, k3 + 4).
+__device__ __forceinline__ int fft_out_column(int t, int h) { return t == 0 ? 128 * h : (h == 0 ? t : 256 - t); }
+
+// stage 3: reads y2 from src; on exit r[h*8 + k3] = Z[fft_out_column(t, h) + 256*k3].
 __device__ __forceinline__ void fft_stage3(float2 (&r)[16], const float2* __restrict__ src, int t) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int pi = t + 128 * h;
+        const int pi = fft_out_column(t, h);
         const float2* col = src + (pi >> 4) * 128 + (pi & 15);
         float2 c[8];
 #pragma unroll

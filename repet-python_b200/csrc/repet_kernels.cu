@@ -23,11 +23,28 @@ namespace repet {
 // (n = n1*128 + t), so the overlap is carried in registers: 16 new samples per thread-frame.
 // Algorithmic bytes per frame: 2*4 KB audio in, 16 KB X out, 4.1 KB P out.
 // ------------------------------------------------------------------------------------------
+// one output bin of the Hermitian split: a = Z[k]/2, b = Z[2048-k]/2 (the window is pre-halved)
+//   XL[k] = a + conj(b)            XR[k] = -i (a - conj(b))
+template <int NCH>
+__device__ __forceinline__ void stft_emit(float2 a, float2 b, int k, float2* __restrict__ xrow, float* __restrict__ prow,
+                                          int pmode) {
+    const float2 xl = __ffma2_rn(b, make_float2(1.f, -1.f), a);
+    xrow[k] = xl;
+    float mean = cmag(xl);
+    if (NCH == 2) {
+        const float2 d = __ffma2_rn(b, make_float2(-1.f, 1.f), a);  // a - conj(b); XR = (d.y, -d.x)
+        xrow[XPITCH + k] = make_float2(d.y, -d.x);
+        mean = 0.5f * (mean + cmag(d));
+    }
+    if (prow) prow[k] = pmode == P_POWER ? mean * mean : mean;
+}
+
 template <int NCH, int MINB>
 __global__ void __launch_bounds__(FFT_THREADS, MINB)
 k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window, FftTables tb,
        float2* __restrict__ X, float* __restrict__ P, int pmode, int K) {
-    __shared__ float2 s_buf[2][FFT_BUF];
+    __shared__ float2 s_bufA[FFT_BUF];
+    __shared__ float2 s_bufB[FFT_BUF];
     __shared__ float2 s_tw2[128];
     const int t = threadIdx.x;
     const int item = blockIdx.y;
@@ -36,91 +53,88 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
     s_tw2[t] = tb.tw2[t];
     Twiddle1 tw;
     tw.load(tb.tw1, t);
-    float wv[16];
+    float wv[16];  // half the window: the 1/2 of the channel split is folded in here
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) wv[n1] = __ldg(&window[n1 * 128 + t]);
+    for (int n1 = 0; n1 < 16; ++n1) wv[n1] = 0.5f * __ldg(&window[n1 * 128 + t]);
     const int gitem = g.item0 + item;
     const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
     const float* __restrict__ a0 = audio + g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
     const float* __restrict__ a1 = a0 + g.chan_stride;
+    // first half of the first frame (raw samples); afterwards it is the previous frame's second half
     float cl[8], cr[8];
+    {
+        const long long base = (long long)(j0 - 1 + g.frame_shift) * HOP + t;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cl[i] = cr[i] = 0.f;
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const long long idx = base + n1 * 128;
+            const bool ok = idx >= 0 && idx < g.S;
+            cl[n1] = ok ? __ldg(a0 + idx) : 0.f;
+            cr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
+        }
+    }
     __syncthreads();
-    int par = 0;
     for (int j = j0; j < j1; ++j) {
         float2 r[16];
-        const long long base = (long long)(j - 1 + g.frame_shift) * HOP + t;
-        const bool carry = j > j0;
+        const long long base = (long long)(j + g.frame_shift) * HOP + t;  // second half of frame j
         // pull the next frame's new half (2 x 4 KB) towards L2 while this frame is transformed
         if (t < 64 && j + 1 < j1) {
-            const long long nxt = (long long)(j + 1 + g.frame_shift) * HOP + (t & 31) * 32;
+            const long long nxt = base - t + HOP + (t & 31) * 32;
             if (nxt < g.S) prefetch_l2((t < 32 || NCH == 1 ? a0 : a1) + nxt);
         }
+        float nl[8], nr[8];
+        if (base - t + HOP <= g.S) {  // whole half frame inside the signal: no bounds checks
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            float xl, xr = 0.f;
-            if (n1 < 8 && carry) {
-                xl = cl[n1];
-                xr = cr[n1];
-            } else {
+            for (int n1 = 0; n1 < 8; ++n1) {
+                nl[n1] = __ldg(a0 + base + n1 * 128);
+                nr[n1] = NCH == 2 ? __ldg(a1 + base + n1 * 128) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
                 const long long idx = base + n1 * 128;
-                const bool ok = idx >= 0 && idx < g.S;
-                xl = ok ? __ldg(a0 + idx) : 0.f;
-                if (NCH == 2) xr = ok ? __ldg(a1 + idx) : 0.f;
+                const bool ok = idx < g.S;
+                nl[n1] = ok ? __ldg(a0 + idx) : 0.f;
+                nr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
             }
-            if (n1 >= 8) {
-                cl[n1 - 8] = xl;
-                cr[n1 - 8] = xr;
-            }
-            r[n1] = make_float2(wv[n1] * xl, wv[n1] * xr);
         }
-        float2* A = s_buf[par];
-        float2* B = s_buf[par ^ 1];
-        fft_stage1(r, tw, A, t);
-        __syncthreads();
-        fft_stage2(r, A, B, s_tw2, t);
-        __syncthreads();
-        fft_stage3(r, B, t);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int k3 = 0; k3 < 8; ++k3) A[t + 128 * h + 256 * k3] = r[h * 8 + k3];
+        for (int n1 = 0; n1 < 8; ++n1) {
+            r[n1] = make_float2(wv[n1] * cl[n1], wv[n1] * cr[n1]);
+            r[8 + n1] = make_float2(wv[8 + n1] * nl[n1], wv[8 + n1] * nr[n1]);
+            cl[n1] = nl[n1];
+            cr[n1] = nr[n1];
+        }
+        fft_stage1(r, tw, s_bufA, t);
         __syncthreads();
+        fft_stage2(r, s_bufA, s_bufB, s_tw2, t);
+        __syncthreads();
+        fft_stage3(r, s_bufB, t);
+        // the thread now holds Z[k]/2 and Z[2048-k]/2 for its 8 bins k < 1024: split in registers
         const size_t frame = (size_t)item * g.T + j;
         float2* __restrict__ xrow = X + frame * (size_t)(NCH * XPITCH);
         float* __restrict__ prow = P ? P + frame * (size_t)PPITCH : nullptr;
+        if (t != 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = t + 128 * i;
-            const float2 a = A[k];
-            float2 xl, xr;
-            float ml, mr;
-            if (k == 0) {
-                const float2 ny = A[1024];
-                xl = make_float2(a.x, ny.x);
-                xr = make_float2(a.y, ny.y);
-                ml = fabsf(a.x);
-                mr = fabsf(a.y);
-                if (prow) {
-                    const float mn = NCH == 2 ? 0.5f * (fabsf(ny.x) + fabsf(ny.y)) : fabsf(ny.x);
-                    prow[1024] = pmode == P_POWER ? mn * mn : mn;
-                }
-            } else {
-                const float2 b = A[2048 - k];
-                xl = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-                xr = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
-                ml = cmag(xl);
-                mr = cmag(xr);
-            }
-            xrow[k] = xl;
-            if (NCH == 2) xrow[XPITCH + k] = xr;
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k3 = 0; k3 < 4; ++k3)
+                    stft_emit<NCH>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3], (h == 0 ? t : 256 - t) + 256 * k3, xrow, prow, pmode);
+        } else {
+            // thread 0 owns the self-mirrored columns 0 and 128; bin 0 packs (DC, Nyquist), both real
+            const float2 dc = r[0], ny = r[4];
+            xrow[0] = make_float2(2.f * dc.x, 2.f * ny.x);
+            if (NCH == 2) xrow[XPITCH] = make_float2(2.f * dc.y, 2.f * ny.y);
             if (prow) {
-                const float mean = NCH == 2 ? 0.5f * (ml + mr) : ml;
-                prow[k] = pmode == P_POWER ? mean * mean : mean;
+                const float m0 = NCH == 2 ? fabsf(dc.x) + fabsf(dc.y) : 2.f * fabsf(dc.x);
+                const float mn = NCH == 2 ? fabsf(ny.x) + fabsf(ny.y) : 2.f * fabsf(ny.x);
+                prow[0] = pmode == P_POWER ? m0 * m0 : m0;
+                prow[XPITCH] = pmode == P_POWER ? mn * mn : mn;
             }
+#pragma unroll
+            for (int k3 = 1; k3 < 4; ++k3) stft_emit<NCH>(r[k3], r[8 - k3], 256 * k3, xrow, prow, pmode);
+#pragma unroll
+            for (int k3 = 0; k3 < 4; ++k3) stft_emit<NCH>(r[8 + k3], r[8 + 7 - k3], 128 + 256 * k3, xrow, prow, pmode);
         }
-        par ^= 1;
     }
 }
 
@@ -210,7 +224,7 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int k3 = 0; k3 < 8; ++k3) out[t + 128 * h + 256 * k3] = acc[h * 8 + k3];
+        for (int k3 = 0; k3 < 8; ++k3) out[fft_out_column(t, h) + 256 * k3] = acc[h * 8 + k3];
 }
 
 static size_t beat_smem_bytes(int t_len, int* TP_out) {
@@ -397,34 +411,35 @@ k_beat_blocked(const float* __restrict__ P, int T, int Bk, int max_lag, FftTable
             fft_stage2(r, s_bufA, s_bufB, s_tw2, t);
             __syncthreads();
             fft_stage3(r, s_bufB, t);
-            // Z in natural order (bufA is free: its readers finished before the last barrier)
+            // Z[k] and Z[-k] are both in this thread's registers (fft_out_column): pair them here
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int k3 = 0; k3 < 8; ++k3) s_bufA[t + 128 * h + 256 * k3] = r[h * 8 + k3];
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = t + 128 * i;
-                const float2 p = s_bufA[k];
-                const float2 zq = s_bufA[(FFT_N - k) & (FFT_N - 1)];
-                const float2 q = make_float2(zq.x, -zq.y);  // conj Z[-k]
-                // conj(A) C = conj(p + q) * (-i) (p - q) / 4
-                const float sx = p.x + q.x, sy = -(p.y + q.y);  // conj(p + q)
-                const float dx = p.y - q.y, dy = -(p.x - q.x);  // -i (p - q)
-                acc_re[i] = fmaf(0.25f, sx * dx - sy * dy, acc_re[i]);
-                acc_im[i] = fmaf(0.25f, sx * dy + sy * dx, acc_im[i]);
-            }
-            // the next row's stage 1 writes bufA: every thread must be done reading it
-            __syncthreads();
+                for (int k3 = 0; k3 < 8; ++k3) {
+                    const float2 p = r[h * 8 + k3];
+                    // mirror of column c, slot k3: column 256-c, slot 7-k3; the self-mirrored columns of
+                    // thread 0 pair (0: k3 <-> (8-k3)%8, 128: k3 <-> 7-k3) inside the same column
+                    float2 zq;
+                    if (t != 0) zq = r[(1 - h) * 8 + 7 - k3];
+                    else zq = (h == 0) ? r[(8 - k3) & 7] : r[8 + 7 - k3];
+                    const float2 q = make_float2(zq.x, -zq.y);  // conj Z[-k]
+                    // conj(A) C = conj(p + q) * (-i) (p - q) / 4
+                    const float sx = p.x + q.x, sy = -(p.y + q.y);  // conj(p + q)
+                    const float dx = p.y - q.y, dy = -(p.x - q.x);  // -i (p - q)
+                    acc_re[h * 8 + k3] = fmaf(0.25f, sx * dx - sy * dy, acc_re[h * 8 + k3]);
+                    acc_im[h * 8 + k3] = fmaf(0.25f, sx * dy + sy * dx, acc_im[h * 8 + k3]);
+                }
         }
     }
     const size_t part = ((size_t)item * n_blocks + blk) * n_fparts + fpart;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        g_re[part * BEAT_L + t + 128 * i] = acc_re[i];
-        g_im[part * BEAT_L + t + 128 * i] = acc_im[i];
-    }
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k3 = 0; k3 < 8; ++k3) {
+            const int k = fft_out_column(t, h) + 256 * k3;
+            g_re[part * BEAT_L + k] = acc_re[h * 8 + k3];
+            g_im[part * BEAT_L + k] = acc_im[h * 8 + k3];
+        }
 }
 
 void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, int Bk, int max_lag, FftTables tb,
@@ -718,7 +733,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k3 = 0; k3 < 4; ++k3) {
-                    const long long m = blk + t + 128 * h + 256 * k3;
+                    const long long m = blk + fft_out_column(t, h) + 256 * k3;
                     if (m < g.S) {
                         o0[m] = (carry_l[h * 4 + k3] + r[h * 8 + k3].y) * scale;
                         if (NCH == 2) o1[m] = (carry_r[h * 4 + k3] + r[h * 8 + k3].x) * scale;
