@@ -330,8 +330,10 @@ def run_b200_arm(args, rank, local_rank, world):
     start = torch.cuda.Event(enable_timing=True)
     end = torch.cuda.Event(enable_timing=True)
     start.record(stream)
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    t_host = time.perf_counter() - t_host  # host time to ENQUEUE the steps (no synchronisation inside)
     end.record(stream)
     torch.cuda.synchronize(device)
     barrier()
@@ -400,6 +402,7 @@ def run_b200_arm(args, rank, local_rank, world):
             "dtype": "f32", "data": "synthetic", "config": config_dict(args), "clocks": clocks,
             "gpu_launches": int(launches), "roofline": roofline,
             "periods_sample": periods_first[:8].tolist(), "synthesis_seconds": t_gen,
+            "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,
         }
         if e2e_ms is not None:
             line["e2e"] = {"value": audio_seconds_per_step * args.steps / (e2e_max_ms / 1e3), "unit": UNIT,

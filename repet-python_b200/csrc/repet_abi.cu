@@ -46,13 +46,15 @@ int check_common(repet_handle* h, const repet_params* p, int n_channels) {
 
 size_t default_ws_limit(repet_handle* h) {
     if (h->ws_limit) return (size_t)h->ws_limit;
+    if (h->ws_auto) return h->ws_auto;  // cudaMemGetInfo is a slow driver call: ask once per handle
     // big chunks win (launch tails and the per-clip period kernel amortise): up to 24 GB, but never
     // more than 40 % of what is free on the device
     size_t free_b = 0, total_b = 0;
     size_t limit = (size_t)24 << 30;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
         limit = std::min(limit, (size_t)((double)(free_b + h->arena_bytes) * 0.4));
-    return std::max(limit, (size_t)256 << 20);
+    h->ws_auto = std::max(limit, (size_t)256 << 20);
+    return h->ws_auto;
 }
 
 }  // namespace repet

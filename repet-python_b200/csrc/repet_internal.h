@@ -25,6 +25,7 @@ struct repet_handle {
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0;
     uint64_t ws_limit = 0;
+    size_t ws_auto = 0;  // cached automatic workspace limit
     uint64_t launches = 0;
     int sm_count = 148;
     // optional per-kernel timing (bench.py's roofline): one event pair per launch

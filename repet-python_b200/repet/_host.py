@@ -239,7 +239,25 @@ def hamming_window(window_length):
     return scipy.signal.windows.hamming(window_length, sym=False)
 
 
+_PARAM_CACHE = {}
+
+
 def derive_params(sampling_frequency, tunables, driver="original"):
+    """Cached front end of _derive_params (the derivation is pure; batch callers hit it every step)."""
+    key = (float(sampling_frequency), driver, tuple((k, tuple(v) if isinstance(v, (list, tuple)) else v)
+                                                    for k, v in sorted(tunables.items())))
+    hit = _PARAM_CACHE.get(key)
+    if hit is None:
+        hit = _derive_params(sampling_frequency, tunables, driver)
+        if len(_PARAM_CACHE) > 64:
+            _PARAM_CACHE.clear()
+        _PARAM_CACHE[key] = hit
+    params = RepetParams()
+    ctypes.memmove(ctypes.byref(params), ctypes.byref(hit[0]), ctypes.sizeof(RepetParams))
+    return params, hit[1]
+
+
+def _derive_params(sampling_frequency, tunables, driver="original"):
     """All derived integers of the five drivers.  `driver` selects the
     unit of the segment sizes: samples for extended (repet.py:266-267), frames for adaptive
     (repet.py:519-520)."""
