@@ -195,6 +195,23 @@ int repet_selfsimilarity(repet_handle* h, const float* magnitude, int n_frames, 
 int repet_periods(repet_handle* h, const double* beat, int n_lags, int n_columns, int period_lo, int period_hi,
                   int32_t* periods);
 
+/* _similaritymatrix / _selfsimilaritymatrix (repet.py:1209-1246) in exact float64: magnitudes
+ * [n_frames1][n_rows], [n_frames2][n_rows] (n_rows <= 1025) -> cosine similarity [n_frames1][n_frames2]. */
+int repet_similarity(repet_handle* h, const float* magnitude1, int n_frames1, const float* magnitude2, int n_frames2,
+                     int n_rows, double* similarity);
+/* _localmaxima (n_columns = 1) / _indices (repet.py:1294-1383) on caller-provided float64 data
+ * [n][n_columns] row-major: per column the indices (and optionally values) of the strict local maxima,
+ * best first; indices/values [n_columns][number_values], counts [n_columns]. */
+int repet_localmaxima(repet_handle* h, const double* data, int n, int n_columns, double minimum_value,
+                      int minimum_distance, int number_values, int32_t* indices, int32_t* counts, double* values);
+/* _simmask (repet.py:1511-1545): magnitudes [n_frames][1025], lists indices[n_frames][number] with
+ * counts[n_frames] -> mask [n_frames][1025]. */
+int repet_simmask(repet_handle* h, const float* magnitude, int n_frames, const int32_t* indices, const int32_t* counts,
+                  int number, float* mask);
+/* _acorr (repet.py:1108-1139): data [n_rows][n_columns] fp32 row-major, 2*n_rows-1 <= 2048 ->
+ * unbiased autocorrelation of every column, float64 [n_rows][n_columns]. */
+int repet_acorr(repet_handle* h, const float* data, int n_rows, int n_columns, double* autocorrelation);
+
 #ifdef __cplusplus
 }
 #endif

@@ -480,4 +480,138 @@ int repet_periods(repet_handle* h, const double* beat, int n_lags, int n_columns
     return REPET_OK;
 }
 
+// upload a [n][n_rows] fp32 matrix into rows of PPITCH floats (zero padded)
+static int upload_rows(repet_handle* h, const float* host, int n, int n_rows, float* dev) {
+    CU(cudaMemsetAsync(dev, 0, (size_t)n * PPITCH * sizeof(float), h->stream));
+    CU(cudaMemcpy2DAsync(dev, PPITCH * sizeof(float), host, n_rows * sizeof(float), n_rows * sizeof(float), n,
+                         cudaMemcpyHostToDevice, h->stream));
+    return REPET_OK;
+}
+
+int repet_similarity(repet_handle* h, const float* magnitude1, int n_frames1, const float* magnitude2, int n_frames2,
+                     int n_rows, double* similarity) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!magnitude1 || !magnitude2 || !similarity || n_frames1 < 1 || n_frames2 < 1 || n_rows < 1 || n_rows > NBIN)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size (n_rows <= 1025)");
+    CU(cudaSetDevice(h->device));
+    const size_t n1 = n_frames1, n2 = n_frames2;
+    const size_t need = align_up((n1 + n2) * PPITCH * sizeof(float)) + align_up((n1 + n2) * APITCH64 * sizeof(double)) +
+                        align_up(n1 * n2 * sizeof(double)) + 1024;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    float* V = bump.take<float>((n1 + n2) * PPITCH);
+    double* An = bump.take<double>((n1 + n2) * APITCH64);
+    double* out = bump.take<double>(n1 * n2);
+    cudaStream_t st = h->stream;
+    if ((rc = upload_rows(h, magnitude1, n_frames1, n_rows, V))) return rc;
+    if ((rc = upload_rows(h, magnitude2, n_frames2, n_rows, V + n1 * PPITCH))) return rc;
+    launch_normalize(st, V, n_frames1 + n_frames2, An, nullptr, 0);
+    launch_cosine64(st, An, n_frames1, An + n1 * APITCH64, n_frames2, out);
+    h->launches += 2;
+    CU(cudaMemcpyAsync(similarity, out, n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_localmaxima(repet_handle* h, const double* data, int n, int n_columns, double minimum_value,
+                      int minimum_distance, int number_values, int32_t* indices, int32_t* counts, double* values) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!data || !indices || !counts || n < 1 || n_columns < 1 || number_values < 1 || minimum_distance < 0)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    CU(cudaSetDevice(h->device));
+    const size_t total = (size_t)n * n_columns, lists = (size_t)n_columns * number_values;
+    const size_t need = align_up(total * sizeof(double)) + align_up(lists * sizeof(int32_t)) +
+                        align_up((size_t)n_columns * sizeof(int32_t)) + align_up(lists * sizeof(double)) + 1024;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    double* d = bump.take<double>(total);
+    int32_t* idx = bump.take<int32_t>(lists);
+    int32_t* cnt = bump.take<int32_t>(n_columns);
+    double* val = bump.take<double>(lists);
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(d, data, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (launch_localmaxima64(st, d, n, n_columns, minimum_value, minimum_distance, number_values, idx, cnt, val))
+        return fail(h, REPET_E_UNSUPPORTED, "vector too long for the shared-memory local-maximum scan");
+    h->launches += 1;
+    CU(cudaMemcpyAsync(indices, idx, lists * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(counts, cnt, (size_t)n_columns * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (values) CU(cudaMemcpyAsync(values, val, lists * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_simmask(repet_handle* h, const float* magnitude, int n_frames, const int32_t* indices, const int32_t* counts,
+                  int number, float* mask) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!magnitude || !indices || !counts || !mask || n_frames < 1 || number < 1)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    CU(cudaSetDevice(h->device));
+    const int T = n_frames;
+    const size_t x_elems = (size_t)T * XPITCH;
+    const size_t need = align_up(x_elems * sizeof(float2)) + 2 * align_up((size_t)T * PPITCH * sizeof(float)) +
+                        align_up((size_t)T * number * sizeof(int32_t)) + align_up((size_t)T * sizeof(int32_t)) + 1024;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    float2* X = bump.take<float2>(x_elems);
+    float* model = bump.take<float>((size_t)T * PPITCH);
+    float* M = bump.take<float>((size_t)T * PPITCH);
+    int32_t* idx = bump.take<int32_t>((size_t)T * number);
+    int32_t* cnt = bump.take<int32_t>(T);
+    std::vector<float2> host;
+    pack_magnitudes(magnitude, T, host);
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(X, host.data(), x_elems * sizeof(float2), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(idx, indices, (size_t)T * number * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cnt, counts, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (launch_simmodel(st, X, 1, T, 1, idx, cnt, number, 0, model))
+        return fail(h, REPET_E_UNSUPPORTED, "lists too long for the shared-memory median");
+    launch_mask_only(st, X, 1, T, 1, nullptr, T, model, M);
+    h->launches += 2;
+    CU(cudaMemcpy2DAsync(mask, NBIN * sizeof(float), M, PPITCH * sizeof(float), NBIN * sizeof(float), T,
+                         cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+int repet_acorr(repet_handle* h, const float* data, int n_rows, int n_columns, double* autocorrelation) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!data || !autocorrelation || n_rows < 1 || n_columns < 1) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    if (2 * n_rows - 1 > BEAT_L) return fail(h, REPET_E_UNSUPPORTED, "more rows than the 2048-point transform holds");
+    CU(cudaSetDevice(h->device));
+    // every column becomes one beat item whose only non-zero frequency row is that column
+    const int chunk = std::max(1, std::min(n_columns, (int)(((size_t)512 << 20) / ((size_t)n_rows * PPITCH * sizeof(float)))));
+    const size_t need = align_up((size_t)chunk * n_rows * PPITCH * sizeof(float)) + align_up((size_t)chunk * BEAT_L * sizeof(float)) +
+                        align_up((size_t)chunk * n_rows * sizeof(double)) + 1024;
+    int rc = ensure_arena(h, need);
+    if (rc) return rc;
+    Bump bump(h->arena);
+    float* P = bump.take<float>((size_t)chunk * n_rows * PPITCH);
+    float* psd = bump.take<float>((size_t)chunk * BEAT_L);
+    double* b = bump.take<double>((size_t)chunk * n_rows);
+    cudaStream_t st = h->stream;
+    std::vector<double> host((size_t)chunk * n_rows);
+    for (int c0 = 0; c0 < n_columns; c0 += chunk) {
+        const int g = std::min(chunk, n_columns - c0);
+        CU(cudaMemsetAsync(P, 0, (size_t)g * n_rows * PPITCH * sizeof(float), st));
+        for (int c = 0; c < g; ++c)  // column c0+c -> item c, frequency row 0
+            CU(cudaMemcpy2DAsync(P + (size_t)c * n_rows * PPITCH, PPITCH * sizeof(float), data + c0 + c,
+                                 n_columns * sizeof(float), sizeof(float), n_rows, cudaMemcpyHostToDevice, st));
+        launch_beat(st, P, g, n_rows, 0, n_rows, 0, 1, tables(h), psd, 1, 8);
+        launch_periods(st, psd, nullptr, g, 1, n_rows, 1.0, 0, 0, 0, n_rows, b, n_rows, nullptr, nullptr);
+        h->launches += 2;
+        CU(cudaMemcpyAsync(host.data(), b, (size_t)g * n_rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int c = 0; c < g; ++c)
+            for (int l = 0; l < n_rows; ++l) autocorrelation[(size_t)l * n_columns + c0 + c] = host[(size_t)c * n_rows + l];
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
 }  // extern "C"

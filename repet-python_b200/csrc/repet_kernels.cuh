@@ -111,6 +111,11 @@ void launch_online_select(cudaStream_t st, const double* An64, int n_items, int 
 int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* idx, const int* cnt,
                     int number, int first_frame, float* model);
 
+// helper-level similarity kernels (exact float64)
+void launch_cosine64(cudaStream_t st, const double* A1, int n1, const double* A2, int n2, double* out);
+int launch_localmaxima64(cudaStream_t st, const double* data, int n, int n_columns, double thr, int d, int number,
+                         int* idx_out, int* cnt_out, double* val_out);
+
 // layout converters for the float64 (S, C) NumPy convention of the reference API
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out);
 void launch_planar_to_f64_interleaved(cudaStream_t st, const float* in, long long S, int C, double* out);

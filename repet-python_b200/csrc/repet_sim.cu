@@ -516,4 +516,80 @@ int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nc
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// k_cosine64  --  _similaritymatrix / _selfsimilaritymatrix as helpers     repet.py:1209-1246
+// Exact float64 cosine similarity of float64-normalised frames: out[i][j] = <A1[i], A2[j]>.
+// One warp per output element (helper sizes only; the drivers use the tensor-core pass).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cosine64(const double* __restrict__ A1, int n1, const double* __restrict__ A2, int n2, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (long long)n1 * n2) return;
+    const int i = (int)(w / n2), j = (int)(w - (long long)i * n2);
+    const double e = warp_dot64(A1 + (size_t)i * APITCH64, A2 + (size_t)j * APITCH64, lane);
+    if (lane == 0) out[(size_t)i * n2 + j] = e;
+}
+
+void launch_cosine64(cudaStream_t st, const double* A1, int n1, const double* A2, int n2, double* out) {
+    const long long threads = (long long)n1 * n2 * 32;
+    k_cosine64<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A1, n1, A2, n2, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_localmaxima64  --  _localmaxima / _indices on caller-provided float64 data
+//                                                                       repet.py:1294-1383
+// Column c of a row-major [n][n_columns] matrix (n_columns = 1: a vector).  The reference's rule
+// verbatim: v[i] >= thr and v[i] > every neighbour within +-d (windows clipped, NaN never wins),
+// survivors ranked by value descending (ties: descending index), first `number` kept.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_localmaxima64(const double* __restrict__ data, int n, int n_columns, double thr, int d, int number,
+                int* __restrict__ idx_out, int* __restrict__ cnt_out, double* __restrict__ val_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* s_v = reinterpret_cast<double*>(smem);          // [n]
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_v + n);  // [n]
+    __shared__ int s_kept;
+    const int c = blockIdx.x, t = threadIdx.x;
+    if (t == 0) s_kept = 0;
+    for (int i = t; i < n; i += blockDim.x) s_v[i] = data[(size_t)i * n_columns + c];
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) {
+        const double v = s_v[i];
+        bool keep = v >= thr;
+        const int lo = max(i - d, 0), hi = min(i + d, n - 1);
+        for (int u = lo; u <= hi && keep; ++u)
+            if (u != i && !(v > s_v[u])) keep = false;
+        s_keep[i] = keep ? 1 : 0;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) {
+        if (!s_keep[i]) continue;
+        const double v = s_v[i];
+        int rank = 0;
+        for (int u = 0; u < n; ++u)
+            if (u != i && s_keep[u]) rank += (s_v[u] > v) || (s_v[u] == v && u > i);
+        atomicAdd(&s_kept, 1);
+        if (rank < number) {
+            idx_out[(size_t)c * number + rank] = i;
+            if (val_out) val_out[(size_t)c * number + rank] = v;
+        }
+    }
+    __syncthreads();
+    if (t == 0) cnt_out[c] = min(s_kept, number);
+}
+
+int launch_localmaxima64(cudaStream_t st, const double* data, int n, int n_columns, double thr, int d, int number,
+                         int* idx_out, int* cnt_out, double* val_out) {
+    const size_t smem = (size_t)n * 9 + 16;
+    if (smem > 220 * 1024) return -1;
+    static size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+        cudaFuncSetAttribute(k_localmaxima64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    k_localmaxima64<<<n_columns, 256, smem, st>>>(data, n, n_columns, thr, d, number, idx_out, cnt_out, val_out);
+    return 0;
+}
+
 }  // namespace repet

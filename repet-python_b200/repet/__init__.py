@@ -224,6 +224,11 @@ def _istft(audio_stft, window_function, step_length):
     return signal[0].astype(float)
 
 
+def _acorr(data_matrix):
+    """Autocorrelation of every column using the Wiener-Khinchin theorem (repet.py:1108-1139)."""
+    return _host.acorr(data_matrix)
+
+
 def _beatspectrum(audio_spectrogram):
     """Beat spectrum (repet.py:1142-1158): (number_frequencies, number_times) -> (number_times,)."""
     return _host.beatspectrum(audio_spectrogram)
@@ -232,6 +237,31 @@ def _beatspectrum(audio_spectrogram):
 def _beatspectrogram(audio_spectrogram, segment_length, segment_step):
     """Beat spectrogram (repet.py:1161-1206): (number_frequencies, number_times) -> (segment_length, number_times)."""
     return _host.beatspectrogram(audio_spectrogram, segment_length, segment_step)
+
+
+def _selfsimilaritymatrix(data_matrix):
+    """Self-similarity matrix using the cosine similarity (repet.py:1209-1225), exact float64."""
+    return _host.similaritymatrix(data_matrix, data_matrix)
+
+
+def _similaritymatrix(data_matrix1, data_matrix2):
+    """Similarity matrix using the cosine similarity (repet.py:1228-1246), exact float64."""
+    return _host.similaritymatrix(data_matrix1, data_matrix2)
+
+
+def _localmaxima(data_vector, minimum_value, minimum_distance, number_values):
+    """Values and indices of the local maxima in a vector (repet.py:1294-1345)."""
+    return _host.localmaxima(data_vector, minimum_value, minimum_distance, number_values)
+
+
+def _indices(similarity_matrix, similarity_threshold, similarity_distance, similarity_number):
+    """Similarity indices from the similarity matrix (repet.py:1348-1383)."""
+    return _host.indices(similarity_matrix, similarity_threshold, similarity_distance, similarity_number)
+
+
+def _simmask(audio_spectrogram, similarity_indices):
+    """Repeating mask for REPET-SIM (repet.py:1511-1545)."""
+    return _host.simmask(audio_spectrogram, similarity_indices)
 
 
 def _periods(beat_spectrogram, period_range):

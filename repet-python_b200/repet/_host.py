@@ -83,6 +83,10 @@ SIGNATURES = {
     "repet_adaptivemask": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp]),
     "repet_beatspectrogram": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "repet_selfsimilarity": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
+    "repet_similarity": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _c_int, _vp]),
+    "repet_localmaxima": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_double, _c_int, _c_int, _vp, _vp, _vp]),
+    "repet_simmask": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _c_int, _vp]),
+    "repet_acorr": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
     "repet_periods": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "repet_sim_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_sim_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
@@ -611,4 +615,71 @@ def selfsimilarity(data_matrix, handle=None):
     number_times, number_rows = magnitude.shape
     out = np.empty((number_times, number_times), dtype=np.float32)
     handle.check(handle.lib.repet_selfsimilarity(handle.h, _ptr(magnitude), number_times, number_rows, _ptr(out)))
+    return out
+
+
+def similaritymatrix(data_matrix1, data_matrix2, handle=None):
+    """_similaritymatrix (repet.py:1228-1246) in exact float64: (F, T1), (F, T2) -> (T1, T2)."""
+    handle = handle or get_handle()
+    m1 = np.ascontiguousarray(np.asarray(data_matrix1).T, dtype=np.float32)
+    m2 = np.ascontiguousarray(np.asarray(data_matrix2).T, dtype=np.float32)
+    if m1.shape[1] != m2.shape[1]:
+        raise ValueError("matrices must have the same number of rows")
+    out = np.empty((m1.shape[0], m2.shape[0]), dtype=np.float64)
+    handle.check(handle.lib.repet_similarity(handle.h, _ptr(m1), m1.shape[0], _ptr(m2), m2.shape[0], m1.shape[1], _ptr(out)))
+    return out
+
+
+def localmaxima(data_vector, minimum_value, minimum_distance, number_values, handle=None):
+    """_localmaxima (repet.py:1294-1345): values and indices of the strict local maxima, best first."""
+    handle = handle or get_handle()
+    data = np.ascontiguousarray(data_vector, dtype=np.float64).reshape(-1, 1)
+    number = max(1, int(number_values))
+    idx = np.zeros((1, number), dtype=np.int32)
+    val = np.zeros((1, number), dtype=np.float64)
+    cnt = np.zeros(1, dtype=np.int32)
+    handle.check(handle.lib.repet_localmaxima(handle.h, _ptr(data), data.shape[0], 1, float(minimum_value),
+                                              int(minimum_distance), number, _ptr(idx), _ptr(cnt), _ptr(val)))
+    n = min(int(cnt[0]), int(number_values))
+    return val[0, :n].copy(), idx[0, :n].astype(np.int64)
+
+
+def indices(similarity_matrix, similarity_threshold, similarity_distance, similarity_number, handle=None):
+    """_indices (repet.py:1348-1383): the local-maximum indices of every column, as a list of arrays."""
+    handle = handle or get_handle()
+    data = np.ascontiguousarray(similarity_matrix, dtype=np.float64)
+    n, columns = data.shape
+    number = max(1, int(similarity_number))
+    idx = np.zeros((columns, number), dtype=np.int32)
+    cnt = np.zeros(columns, dtype=np.int32)
+    handle.check(handle.lib.repet_localmaxima(handle.h, _ptr(data), n, columns, float(similarity_threshold),
+                                              int(similarity_distance), number, _ptr(idx), _ptr(cnt), None))
+    return [idx[c, : min(int(cnt[c]), int(similarity_number))].astype(np.int64) for c in range(columns)]
+
+
+def simmask(audio_spectrogram, similarity_indices, handle=None):
+    """_simmask (repet.py:1511-1545): (1025, T) magnitudes + list of index arrays -> float64 (1025, T)."""
+    handle = handle or get_handle()
+    magnitude = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
+    number_times, number_frequencies = magnitude.shape
+    if number_frequencies != 1025:
+        raise NotImplementedError("this build masks 1025-bin spectrograms (window_length 2048)")
+    number = max(1, max((len(v) for v in similarity_indices), default=1))
+    idx = np.zeros((number_times, number), dtype=np.int32)
+    cnt = np.zeros(number_times, dtype=np.int32)
+    for i, values in enumerate(similarity_indices):
+        cnt[i] = len(values)
+        idx[i, : len(values)] = values
+    out = np.empty((number_times, number_frequencies), dtype=np.float32)
+    handle.check(handle.lib.repet_simmask(handle.h, _ptr(magnitude), number_times, _ptr(idx), _ptr(cnt), number, _ptr(out)))
+    return out.T.astype(np.float64)
+
+
+def acorr(data_matrix, handle=None):
+    """_acorr (repet.py:1108-1139): unbiased autocorrelation of every column, (rows, cols) -> float64."""
+    handle = handle or get_handle()
+    data = np.ascontiguousarray(data_matrix, dtype=np.float32)
+    rows, columns = data.shape
+    out = np.empty((rows, columns), dtype=np.float64)
+    handle.check(handle.lib.repet_acorr(handle.h, _ptr(data), rows, columns, _ptr(out)))
     return out
