@@ -113,6 +113,7 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
         const size_t frame = (size_t)item * g.T + j;
         float2* __restrict__ xrow = X + frame * (size_t)(NCH * XPITCH);
         float* __restrict__ prow = P ? P + frame * (size_t)PPITCH : nullptr;
+        if (prow && t >= 1 && t < PPITCH - XPITCH) prow[XPITCH + t] = 0.f;  // rows 1025..1031: zero padding
         if (t != 0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -165,6 +166,16 @@ void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const flo
 // The CTA stages an 8-row x R tile of P (32 B per frame row: full sectors) transposed in
 // shared memory.  Algorithmic bytes: P read once (4.1 KB per frame).
 // ------------------------------------------------------------------------------------------
+// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (frames outside the clip)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(FFT_THREADS)
 k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step, int n_seg, FftTables tb,
        float* __restrict__ psd_part, int n_parts, int f_per_part, int TP) {
@@ -172,7 +183,7 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
     float2* s_bufA = reinterpret_cast<float2*>(s_raw);
     float2* s_bufB = s_bufA + FFT_BUF;
     float2* s_tw2 = s_bufB + FFT_BUF;
-    float2* s_tile = s_tw2 + 128;  // [4][TP]
+    float4* s_tile = reinterpret_cast<float4*>(s_tw2 + 128);  // 2 x [TP] frames x 4 rows (16 B per frame)
     const int t = threadIdx.x;
     const int bi = blockIdx.y;
     const int item = bi / n_seg, sg = bi - item * n_seg;
@@ -186,30 +197,36 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     const float* __restrict__ Pitem = P + (size_t)item * T * PPITCH;
-    for (int f0 = f_begin; f0 < f_end; f0 += 8) {
-        for (int idx = t; idx < 2 * t_len; idx += FFT_THREADS) {
-            const int row = idx >> 1, half = idx & 1;
+    // tiles of 4 rows x t_len frames, double buffered with cp.async: tile i+1 streams in while the
+    // two transforms of tile i run.  Rows >= 1025 are the zero padding of P.
+    auto fetch = [&](int f0, int buf) {
+        float4* dst = s_tile + buf * TP;
+        for (int row = t; row < t_len; row += FFT_THREADS) {
             const int frame = ts + row;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (frame >= 0 && frame < T)
-                v = __ldg(reinterpret_cast<const float4*>(Pitem + (size_t)frame * PPITCH + f0 + 4 * half));
-            const int f = f0 + 4 * half;
-            if (f + 0 >= f_end) v.x = 0.f;
-            if (f + 1 >= f_end) v.y = 0.f;
-            if (f + 2 >= f_end) v.z = 0.f;
-            if (f + 3 >= f_end) v.w = 0.f;
-            s_tile[(2 * half) * TP + row] = make_float2(v.x, v.y);
-            s_tile[(2 * half + 1) * TP + row] = make_float2(v.z, v.w);
+            const bool ok = frame >= 0 && frame < T;
+            cp_async16(dst + row, Pitem + (size_t)(ok ? frame : 0) * PPITCH + f0, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+    const int n_tiles = (f_end - f_begin + 3) >> 2;
+    if (n_tiles > 0) fetch(f_begin, 0);
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int f0 = f_begin + 4 * tile;
+        if (tile + 1 < n_tiles) {
+            fetch(f0 + 4, (tile + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
-        const int npairs = (min(8, f_end - f0) + 1) >> 1;
+        const float* __restrict__ cur = reinterpret_cast<const float*>(s_tile + (tile & 1) * TP);
+        const int npairs = (min(4, f_end - f0) + 1) >> 1;
         for (int pr = 0; pr < npairs; ++pr) {
             float2 r[16];
-            const float2* __restrict__ col = s_tile + pr * TP;
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
                 const int n = n1 * 128 + t;
-                r[n1] = n < t_len ? col[n] : make_float2(0.f, 0.f);
+                r[n1] = n < t_len ? *reinterpret_cast<const float2*>(cur + 4 * n + 2 * pr) : make_float2(0.f, 0.f);
             }
             fft_stage1(r, tw, s_bufA, t);
             __syncthreads();
@@ -219,6 +236,7 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = fmaf(r[i].x, r[i].x, fmaf(r[i].y, r[i].y, acc[i]));
         }
+        // the buffer just consumed is refilled two iterations from now, after the barriers above
     }
     float* __restrict__ out = psd_part + ((size_t)bi * n_parts + blockIdx.x) * BEAT_L;
 #pragma unroll
@@ -228,9 +246,9 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
 }
 
 static size_t beat_smem_bytes(int t_len, int* TP_out) {
-    int TP = ((t_len + 7) / 8) * 8 + 4;
+    int TP = ((t_len + 7) / 8) * 8 + 8;
     *TP_out = TP;
-    return (size_t)(2 * FFT_BUF + 128 + 4 * TP) * sizeof(float2);
+    return (size_t)(2 * FFT_BUF + 128) * sizeof(float2) + (size_t)2 * TP * sizeof(float4);
 }
 
 void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
