@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "librepet_b200.so")
 SOURCES = ["repet_kernels.cu", "repet_sim.cu", "repet_simgemm.cu", "repet_abi.cu", "repet_drivers.cu"]
-HEADERS = ["repet_kernels.cuh", "fft2048.cuh", "median_networks.cuh", "repet_internal.h", os.path.join("..", "..", "include", "repet_b200.h")]
+HEADERS = ["repet_kernels.cuh", "fft2048.cuh", "median_networks.cuh", "median_networks_large.cuh", "repet_internal.h", os.path.join("..", "..", "include", "repet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

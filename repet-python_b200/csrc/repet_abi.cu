@@ -431,21 +431,24 @@ int repet_selfsimilarity(repet_handle* h, const float* magnitude, int n_frames, 
         return fail(h, REPET_E_INVALID_ARG, "bad buffer or size (n_rows <= 1025)");
     CU(cudaSetDevice(h->device));
     const int T = n_frames;
-    const size_t need = align_up((size_t)T * PPITCH * sizeof(float)) + align_up((size_t)T * KPAD * sizeof(float)) +
+    const size_t need = align_up((size_t)T * PPITCH * sizeof(float)) + 2 * align_up((size_t)T * KPAD * sizeof(float)) +
                         align_up((size_t)T * T * sizeof(float)) + 512;
     int rc = ensure_arena(h, need);
     if (rc) return rc;
     Bump bump(h->arena);
     float* V = bump.take<float>((size_t)T * PPITCH);
     float* An32 = bump.take<float>((size_t)T * KPAD);
+    float* An32lo = bump.take<float>((size_t)T * KPAD);
     float* S = bump.take<float>((size_t)T * T);
     cudaStream_t st = h->stream;
     CU(cudaMemsetAsync(V, 0, (size_t)T * PPITCH * sizeof(float), st));
     CU(cudaMemcpy2DAsync(V, PPITCH * sizeof(float), magnitude, n_rows * sizeof(float), n_rows * sizeof(float), T,
                          cudaMemcpyHostToDevice, st));
-    launch_normalize(st, V, T, nullptr, An32, g_tuning.simgemm_tc ? 1 : 0);
+    const bool split = g_tuning.simgemm_tc >= 2;
+    launch_normalize(st, V, T, nullptr, An32, split ? An32lo : nullptr, g_tuning.simgemm_tc ? 1 : 0);
     if (g_tuning.simgemm_tc) {
-        if (launch_selfsim_tc(st, An32, 1, T, S, h->sm_count)) return fail(h, REPET_E_CUDA, "tensor-map encode failed");
+        if (launch_selfsim_tc(st, An32, split ? An32lo : nullptr, 1, T, S, h->sm_count))
+            return fail(h, REPET_E_CUDA, "tensor-map encode failed");
     } else {
         launch_selfsim_simt(st, An32, 1, T, S);
     }
@@ -506,7 +509,7 @@ int repet_similarity(repet_handle* h, const float* magnitude1, int n_frames1, co
     cudaStream_t st = h->stream;
     if ((rc = upload_rows(h, magnitude1, n_frames1, n_rows, V))) return rc;
     if ((rc = upload_rows(h, magnitude2, n_frames2, n_rows, V + n1 * PPITCH))) return rc;
-    launch_normalize(st, V, n_frames1 + n_frames2, An, nullptr, 0);
+    launch_normalize(st, V, n_frames1 + n_frames2, An, nullptr, nullptr, 0);
     launch_cosine64(st, An, n_frames1, An + n1 * APITCH64, n_frames2, out);
     h->launches += 2;
     CU(cudaMemcpyAsync(similarity, out, n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -552,7 +555,7 @@ int repet_simmask(repet_handle* h, const float* magnitude, int n_frames, const i
     CU(cudaSetDevice(h->device));
     const int T = n_frames;
     const size_t x_elems = (size_t)T * XPITCH;
-    const size_t need = align_up(x_elems * sizeof(float2)) + 2 * align_up((size_t)T * PPITCH * sizeof(float)) +
+    const size_t need = align_up(x_elems * sizeof(float2)) + 3 * align_up((size_t)T * PPITCH * sizeof(float)) +
                         align_up((size_t)T * number * sizeof(int32_t)) + align_up((size_t)T * sizeof(int32_t)) + 1024;
     int rc = ensure_arena(h, need);
     if (rc) return rc;
@@ -560,6 +563,7 @@ int repet_simmask(repet_handle* h, const float* magnitude, int n_frames, const i
     float2* X = bump.take<float2>(x_elems);
     float* model = bump.take<float>((size_t)T * PPITCH);
     float* M = bump.take<float>((size_t)T * PPITCH);
+    float* Vsq = bump.take<float>((size_t)T * PPITCH);
     int32_t* idx = bump.take<int32_t>((size_t)T * number);
     int32_t* cnt = bump.take<int32_t>(T);
     std::vector<float2> host;
@@ -568,7 +572,8 @@ int repet_simmask(repet_handle* h, const float* magnitude, int n_frames, const i
     CU(cudaMemcpyAsync(X, host.data(), x_elems * sizeof(float2), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(idx, indices, (size_t)T * number * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(cnt, counts, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (launch_simmodel(st, X, 1, T, 1, idx, cnt, number, 0, model))
+    launch_sqmag(st, X, T, Vsq);
+    if (launch_simmodel(st, X, Vsq, 1, T, 1, idx, cnt, number, 0, model))
         return fail(h, REPET_E_UNSUPPORTED, "lists too long for the shared-memory median");
     launch_mask_only(st, X, 1, T, 1, nullptr, T, model, M);
     h->launches += 2;

@@ -20,6 +20,10 @@ constexpr float TAU_FP32_GEMM = 1e-4f;
 // TF32 tensor-core pass: operands rounded to nearest TF32 (2^-11 each, products of unit vectors:
 // <= 2 * 2^-11 ~ 9.8e-4) plus the fp32 accumulation of 1056 products inside the tensor core
 constexpr float TAU_TF32_GEMM = 1.5e-3f;
+// 3xTF32 split pass: dropped lo lo^T term and hi + lo representation error (2 * 2^-22) plus the fp32
+// accumulation of 3 x 132 MMAs in the tensor core, each assumed to round the running sum (<= 1) once:
+// 396 * 2^-23 ~ 4.7e-5 worst case; observed ~1e-6 (tests/test_gpu_sim.py)
+constexpr float TAU_3XTF32_GEMM = 1.0e-4f;
 
 // ---------------------------------------------------------------------------------------------
 // the period pipeline shared by `original` and the segments of `extended`:
@@ -254,8 +258,9 @@ int make_plan(repet_handle* h, int kind, const repet_params* p, int nch, int64_t
         b += align_up((size_t)T * plan->number * sizeof(int32_t));  // idx
         b += align_up((size_t)T * sizeof(int32_t));                 // cnt
         b += align_up((size_t)nch * T * PPITCH * sizeof(float));    // model
+        if (plan->number > 32) b += align_up((size_t)nch * T * PPITCH * sizeof(float));  // squared magnitudes
         if (kind == KIND_SIM) {
-            b += align_up((size_t)T * KPAD * sizeof(float));  // An32
+            b += 2 * align_up((size_t)T * KPAD * sizeof(float));  // An32 hi, lo
             b += align_up((size_t)T * T * sizeof(float));     // S
         }
         b += 2048;
@@ -293,8 +298,11 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         int32_t* idx = bump.take<int32_t>((size_t)g * T * plan.number);
         int32_t* cnt = bump.take<int32_t>((size_t)g * T);
         float* model = bump.take<float>((size_t)g * nch * T * PPITCH);
+        float* Vsq = plan.number > 32 ? bump.take<float>((size_t)g * nch * T * PPITCH) : nullptr;
         int32_t* overflow = bump.take<int32_t>(4);  // [overflow flag, candidates, uncertain, neighbour dots]
         float* An32 = online ? nullptr : bump.take<float>((size_t)g * T * KPAD);
+        float* An32lo = online ? nullptr : bump.take<float>((size_t)g * T * KPAD);
+        const int fast = g_tuning.simgemm_tc;
         float* S = online ? nullptr : bump.take<float>((size_t)g * T * T);
         Geom geom = clip_geom(g, nch, plan.S, T);
         geom.first_offset = (long long)clip0 * geom.clip_stride;
@@ -309,7 +317,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         }
         {
             Timed timed(h, REPET_K_NORMALIZE);
-            launch_normalize(st, V, g * T, An64, An32, g_tuning.simgemm_tc ? 1 : 0);
+            launch_normalize(st, V, g * T, An64, An32, fast >= 2 ? An32lo : nullptr, fast ? 1 : 0);
         }
         CU(cudaMemsetAsync(cnt, 0, (size_t)g * T * sizeof(int32_t), st));
         if (online) {
@@ -319,8 +327,8 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         } else {
             {
                 Timed timed(h, REPET_K_SIMGEMM);
-                if (g_tuning.simgemm_tc) {
-                    if (launch_selfsim_tc(st, An32, g, T, S, h->sm_count))
+                if (fast) {
+                    if (launch_selfsim_tc(st, An32, fast >= 2 ? An32lo : nullptr, g, T, S, h->sm_count))
                         return fail(h, REPET_E_CUDA, "tensor-map encode failed for the similarity GEMM");
                 } else {
                     launch_selfsim_simt(st, An32, g, T, S);
@@ -328,13 +336,14 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
             }
             CU(cudaMemsetAsync(overflow, 0, 4 * sizeof(int32_t), st));
             Timed timed(h, REPET_K_TOPK);
-            if (launch_topk(st, S, An64, g, T, g_tuning.simgemm_tc ? TAU_TF32_GEMM : TAU_FP32_GEMM, plan.p.similarity_threshold, plan.distance, plan.number,
+            if (launch_topk(st, S, An64, g, T, fast >= 2 ? TAU_3XTF32_GEMM : (fast ? TAU_TF32_GEMM : TAU_FP32_GEMM), plan.p.similarity_threshold, plan.distance, plan.number,
                             idx, cnt, overflow))
                 return fail(h, REPET_E_UNSUPPORTED, "track too long for the in-shared-memory similarity row");
         }
         {
             Timed timed(h, REPET_K_MODEL);
-            if (launch_simmodel(st, X, g, T, nch, idx, cnt, plan.number, geom.first_frame, model))
+            if (Vsq) launch_sqmag(st, X, (long long)g * T * nch, Vsq);
+            if (launch_simmodel(st, X, Vsq, g, T, nch, idx, cnt, plan.number, geom.first_frame, model))
                 return fail(h, REPET_E_UNSUPPORTED, "similarity_number too large for the shared-memory median");
         }
         {

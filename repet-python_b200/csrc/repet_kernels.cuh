@@ -48,7 +48,7 @@ struct Tuning {
     int mask_minb = 5;       // same for the mask+ISTFT kernel
     int frames_per_cta = 0;  // 0 = pick from the batch size
     int beat_parts = 0;      // 0 = pick from the batch size
-    int simgemm_tc = 1;      // 1 = tcgen05 TF32 similarity GEMM, 0 = fp32 CUDA-core cross-check kernel
+    int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
 };
 extern Tuning g_tuning;
 
@@ -100,16 +100,19 @@ void launch_argmax_columns(cudaStream_t st, const double* beat, int n_lags, int 
                            int* period);
 
 // REPET-SIM (repet_sim.cu)
-void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, int round_tf32);
+void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, float* An32lo,
+                      int round_tf32);
 // tcgen05 / TMEM / TMA self-similarity GEMM (repet_simgemm.cu); returns 0 on success
-int launch_selfsim_tc(cudaStream_t st, const float* An32, int n_items, int T, float* S, int sm_count);
+int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_items, int T, float* S, int sm_count);
 void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
                 int number, int* idx_out, int* cnt_out, int* overflow);
 void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, double thr, int d, int number,
                           int* idx_out, int* cnt_out);
-int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* idx, const int* cnt,
-                    int number, int first_frame, float* model);
+void launch_sqmag(cudaStream_t st, const float2* X, long long n_rows, float* Vsq);
+// Vsq (squared magnitudes [item][T][nch][PPITCH]) is required when number > 32
+int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_items, int T, int nch, const int* idx,
+                    const int* cnt, int number, int first_frame, float* model);
 
 // helper-level similarity kernels (exact float64)
 void launch_cosine64(cudaStream_t st, const double* A1, int n1, const double* A2, int n2, double* out);

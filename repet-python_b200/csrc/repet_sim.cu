@@ -5,6 +5,7 @@
 #include "repet_kernels.cuh"
 #include "fft2048.cuh"
 #include "median_networks.cuh"
+#include "median_networks_large.cuh"
 
 #include <algorithm>
 
@@ -18,7 +19,8 @@ namespace repet {
 // An all-zero frame gives 0/0 = NaN as in the reference (quirk Q18).   One warp per frame.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_normalize(const float* __restrict__ V, int n_rows, double* __restrict__ An64, float* __restrict__ An32, int round_tf32) {
+k_normalize(const float* __restrict__ V, int n_rows, double* __restrict__ An64, float* __restrict__ An32,
+            float* __restrict__ An32lo, int round_tf32) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_rows) return;
     const float* __restrict__ v = V + (size_t)warp * PPITCH;
@@ -38,15 +40,21 @@ k_normalize(const float* __restrict__ V, int n_rows, double* __restrict__ An64, 
             if (round_tf32) {  // round-to-nearest TF32 here, so the tensor core's operand truncation is exact
                 uint32_t bits;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(f));
-                f = __uint_as_float(bits);
+                const float hi = __uint_as_float(bits);
+                if (An32lo) {  // 3xTF32: the residual, itself rounded to TF32 (a ~ hi + lo to 2^-22)
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"((float)(a - (double)hi)));
+                    An32lo[(size_t)warp * KPAD + k] = __uint_as_float(bits);
+                }
+                f = hi;
             }
             An32[(size_t)warp * KPAD + k] = f;
         }
     }
 }
 
-void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, int round_tf32) {
-    k_normalize<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(V, n_rows, An64, An32, round_tf32);
+void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, float* An32lo,
+                      int round_tf32) {
+    k_normalize<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(V, n_rows, An64, An32, An32lo, round_tf32);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -107,10 +115,21 @@ void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T,
     k_selfsim_simt<<<grid, 256, 0, st>>>(An32, T, S);
 }
 
-// exact float64 dot product of two normalised frames, one warp (result in every lane)
+// exact float64 dot product of two normalised frames, one warp (result in every lane).  All 33 loads
+// of the global operand are issued before the first multiply so that their latencies overlap.
 __device__ __forceinline__ double warp_dot64(const double* __restrict__ a, const double* __restrict__ b, int lane) {
+    double bv[33];
+#pragma unroll
+    for (int i = 0; i < 33; ++i) {
+        const int k = lane + 32 * i;
+        bv[i] = k < NBIN ? __ldg(b + k) : 0.0;
+    }
     double s = 0.0;
-    for (int k = lane; k < NBIN; k += 32) s = fma(a[k], b[k], s);
+#pragma unroll
+    for (int i = 0; i < 33; ++i) {
+        const int k = lane + 32 * i;
+        if (k < NBIN) s = fma(a[k], bv[i], s);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
@@ -130,8 +149,8 @@ __device__ __forceinline__ double warp_dot64(const double* __restrict__ a, const
 // NaN never a maximum: quirk Q7).
 // ------------------------------------------------------------------------------------------
 constexpr int TOPK_THREADS = 512;
-constexpr int TOPK_CAP = 4096;       // candidates per column held in shared memory
-constexpr int TOPK_CHUNK = 8192;     // elements of the fast row resident at a time (3 arrays)
+constexpr int TOPK_CAP = 2048;       // candidates per column held in shared memory
+constexpr int TOPK_CHUNK = 4096;     // elements of the fast row resident at a time (3 arrays); 88 KB -> 2 CTAs/SM
 
 __global__ void __launch_bounds__(TOPK_THREADS)
 k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, float tau, double thr, int d, int number,
@@ -220,9 +239,22 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
         count = TOPK_CAP;
     }
     if (t == 0) atomicAdd(overflow + 1, count);  // statistics: candidates proposed
-    // ---- exact values of every candidate -------------------------------------------------------
+    // ---- which candidates need their exact value? ---------------------------------------------
+    // the uncertain ones (local-maximum test within 2 tau) and every pair whose fast values are within
+    // 2 tau of each other (their ORDER is not decided by the fast pass); bit 29 marks them
+    for (int q = t; q < count; q += blockDim.x) {
+        int code = s_cand[q];
+        bool need = (code & (1 << 30)) != 0;
+        const float v = s_vc[q];
+        for (int r = 0; r < count && !need; ++r)
+            if (r != q && fabsf(s_vc[r] - v) <= two_tau) need = true;
+        if (need) s_cand[q] = code | (1 << 29);
+    }
+    __syncthreads();
     for (int q = warp; q < count; q += nwarp) {
-        const int i = s_cand[q] & 0x3fffffff;
+        const int code = s_cand[q];
+        if (!(code & (1 << 29))) continue;
+        const int i = code & 0x1fffffff;
         const double e = warp_dot64(s_col, A + (size_t)i * APITCH64, lane);
         if (lane == 0) s_exact[q] = e;
     }
@@ -231,7 +263,7 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     for (int q = warp; q < count; q += nwarp) {
         const int code = s_cand[q];
         if (!(code & (1 << 30))) continue;
-        const int i = code & 0x3fffffff;
+        const int i = code & 0x1fffffff;
         const double e = s_exact[q];
         const float v = s_vc[q];
         bool keep = e >= thr;
@@ -252,19 +284,26 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
         if (lane == 0 && !keep) s_cand[q] = -1;
     }
     __syncthreads();
-    // ---- rank the survivors by exact value ------------------------------------------------------
+    // ---- rank the survivors: fast values decide when they differ by more than 2 tau, exact values
+    // (both are available then) otherwise; ties by descending index -----------------------------
     for (int q = t; q < count; q += blockDim.x) {
         const int code = s_cand[q];
         if (code < 0) continue;
-        const int i = code & 0x3fffffff;
+        const int i = code & 0x1fffffff;
+        const float v = s_vc[q];
         const double e = s_exact[q];
         int rank = 0;
         for (int r = 0; r < count; ++r) {
             const int other = s_cand[r];
             if (other < 0 || r == q) continue;
-            const double eo = s_exact[r];
-            const int io = other & 0x3fffffff;
-            rank += (eo > e) || (eo == e && io > i);
+            const float vo = s_vc[r];
+            if (fabsf(vo - v) > two_tau) {
+                rank += vo > v;
+            } else {
+                const double eo = s_exact[r];
+                const int io = other & 0x1fffffff;
+                rank += (eo > e) || (eo == e && io > i);
+            }
         }
         atomicAdd(&s_kept, 1);
         if (rank < number) idx_out[((size_t)item * T + c) * (size_t)number + rank] = i;
@@ -299,64 +338,96 @@ int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items
 // Similarities are exact float64 dots of the float64-normalised frames, so the local-maximum
 // rule and the ranking need no certification.  Writes FRAME indices.
 // ------------------------------------------------------------------------------------------
+constexpr int ONLINE_FB = 8;  // target frames per CTA
+
 __global__ void __launch_bounds__(256)
 k_online_select(const double* __restrict__ An64, int T, int B, double thr, int d, int number, int* __restrict__ idx_out,
                 int* __restrict__ cnt_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* s_col = reinterpret_cast<double*>(smem);  // [APITCH64]
-    double* s_sim = s_col + APITCH64;                 // [B]
-    int* s_keep = reinterpret_cast<int*>(s_sim + B);  // [B]
-    __shared__ int s_kept;
+    double* s_tgt = reinterpret_cast<double*>(smem);          // [ONLINE_FB][APITCH64]  target frames
+    double* s_sim = s_tgt + ONLINE_FB * APITCH64;             // [ONLINE_FB][B]         similarity by ring slot
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_sim + ONLINE_FB * B);  // [ONLINE_FB][B]
+    __shared__ int s_kept[ONLINE_FB];
     const int item = blockIdx.y;
-    const int j = blockIdx.x + (B - 1);
-    if (j >= T) return;
+    const int j_first = blockIdx.x * ONLINE_FB + (B - 1);
+    const int nf = min(ONLINE_FB, T - j_first);  // target frames of this CTA
+    if (nf <= 0) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const double* __restrict__ A = An64 + (size_t)item * T * APITCH64;
-    const int j0 = j % B;
-    if (t == 0) s_kept = 0;
-    for (int k = t; k < APITCH64; k += blockDim.x) s_col[k] = A[(size_t)j * APITCH64 + k];
+    if (t < ONLINE_FB) s_kept[t] = 0;
+    for (int k = t; k < nf * APITCH64; k += blockDim.x) s_tgt[k] = A[(size_t)j_first * APITCH64 + k];
     __syncthreads();
-    for (int b = warp; b < B; b += nwarp) {
-        const int frame = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
-        const double e = warp_dot64(s_col, A + (size_t)frame * APITCH64, lane);
-        if (lane == 0) s_sim[b] = e;
+    // Frame u sits in ring slot u mod B.  Every buffer frame of the block's targets is read ONCE and
+    // dotted (exact float64) against all the targets it belongs to: u in [j-B+1, j].
+    const int u_lo = j_first - (B - 1), u_hi = j_first + nf - 1;
+    for (int u = u_lo + warp; u <= u_hi; u += nwarp) {
+        double a[33];
+        const double* __restrict__ row = A + (size_t)u * APITCH64;
+#pragma unroll
+        for (int i = 0; i < 33; ++i) {
+            const int k = lane + 32 * i;
+            a[i] = k < NBIN ? row[k] : 0.0;
+        }
+        const int slot = u % B;
+        for (int f = 0; f < nf; ++f) {
+            const int j = j_first + f;
+            if (u > j || u < j - (B - 1)) continue;  // warp-uniform
+            const double* __restrict__ tg = s_tgt + f * APITCH64;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 33; ++i) {
+                const int k = lane + 32 * i;
+                if (k < NBIN) s = fma(a[i], tg[k], s);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) s_sim[f * B + slot] = s;
+        }
     }
     __syncthreads();
-    for (int b = t; b < B; b += blockDim.x) {
-        const double v = s_sim[b];
+    // strict local maxima in slot order, windows clipped at slots 0 and B-1 (not circular), quirk Q6
+    for (int e = t; e < nf * B; e += blockDim.x) {
+        const int f = e / B, b = e - f * B;
+        const double* __restrict__ sim = s_sim + f * B;
+        const double v = sim[b];
         bool keep = v >= thr;
         const int lo = max(b - d, 0), hi = min(b + d, B - 1);
-        for (int u = lo; u <= hi && keep; ++u)
-            if (u != b && !(v > s_sim[u])) keep = false;
-        s_keep[b] = keep ? 1 : 0;
+        for (int x = lo; x <= hi && keep; ++x)
+            if (x != b && !(v > sim[x])) keep = false;
+        s_keep[e] = keep ? 1 : 0;
     }
     __syncthreads();
-    for (int b = t; b < B; b += blockDim.x) {
-        if (!s_keep[b]) continue;
-        const double v = s_sim[b];
+    for (int e = t; e < nf * B; e += blockDim.x) {
+        if (!s_keep[e]) continue;
+        const int f = e / B, b = e - f * B;
+        const double* __restrict__ sim = s_sim + f * B;
+        const unsigned char* __restrict__ keepf = s_keep + f * B;
+        const double v = sim[b];
         int rank = 0;
-        for (int u = 0; u < B; ++u)
-            if (u != b && s_keep[u]) rank += (s_sim[u] > v) || (s_sim[u] == v && u > b);
-        atomicAdd(&s_kept, 1);
+        for (int x = 0; x < B; ++x)
+            if (x != b && keepf[x]) rank += (sim[x] > v) || (sim[x] == v && x > b);
+        atomicAdd(&s_kept[f], 1);
         if (rank < number) {
+            const int j = j_first + f, j0 = j % B;
             const int frame = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
             idx_out[((size_t)item * T + j) * (size_t)number + rank] = frame;
         }
     }
     __syncthreads();
-    if (t == 0) cnt_out[(size_t)item * T + j] = min(s_kept, number);
+    if (t < nf) cnt_out[(size_t)item * T + j_first + t] = min(s_kept[t], number);
 }
 
 void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, double thr, int d, int number,
                           int* idx_out, int* cnt_out) {
     if (T < B) return;
-    const size_t smem = (size_t)APITCH64 * 8 + (size_t)B * 12;
+    const size_t smem = (size_t)ONLINE_FB * APITCH64 * 8 + (size_t)ONLINE_FB * B * 9 + 16;
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
         cudaFuncSetAttribute(k_online_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    dim3 grid(T - (B - 1), n_items);
+    const int n_targets = T - (B - 1);
+    dim3 grid((n_targets + ONLINE_FB - 1) / ONLINE_FB, n_items);
     k_online_select<<<grid, 256, smem, st>>>(An64, T, B, thr, d, number, idx_out, cnt_out);
 }
 
@@ -440,9 +511,83 @@ __device__ __forceinline__ float tile_median(float* __restrict__ tile, int n, in
 
 constexpr int SIMMODEL_THREADS = 256;
 
+// squared magnitudes of every (frame, channel) row, [rows][PPITCH]: bin 0 = DC^2, bin 1024 = Nyquist^2.
+// Long similar-frame lists gather these 4-byte values instead of the 8-byte spectra.
+__global__ void __launch_bounds__(256)
+k_sqmag(const float2* __restrict__ X, long long n_rows, float* __restrict__ Vsq) {
+    const long long row = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (row >= n_rows || k > XPITCH) return;
+    const float2* __restrict__ x = X + row * XPITCH;
+    float v;
+    if (k == 0) {
+        const float a = __ldg(&x[0]).x;
+        v = __fmul_rn(a, a);
+    } else if (k == XPITCH) {
+        const float a = __ldg(&x[0]).y;
+        v = __fmul_rn(a, a);
+    } else {
+        v = cmag2(__ldg(&x[k]));
+    }
+    Vsq[row * PPITCH + k] = v;
+}
+
+void launch_sqmag(cudaStream_t st, const float2* X, long long n_rows, float* Vsq) {
+    dim3 grid(5, (unsigned)n_rows);
+    k_sqmag<<<grid, 256, 0, st>>>(X, n_rows, Vsq);
+}
+
+// median of n (<= NS) squared magnitudes gathered straight into registers: slots 0..n-1 hold data,
+// the rest is padded with floor((NS-n)/2) times -inf and the remainder +inf, so that the median sits
+// at sorted positions NS/2-1 (odd n) or NS/2-1, NS/2 (even n) whatever n is.
+template <int NS>
+__device__ __forceinline__ float gather_median_large(const float* __restrict__ vchan, size_t vrow,
+                                                     const int* __restrict__ list, int n, int k) {
+    float v[NS];
+    const int lo = (NS - n) >> 1;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (s < n) v[s] = __ldg(vchan + (size_t)list[s] * vrow + k);
+        else v[s] = (s - n) < lo ? -INFINITY : INFINITY;
+    }
+    median_select<NS>(v);
+    return (n & 1) ? fast_sqrt(v[NS / 2 - 1]) : 0.5f * (fast_sqrt(v[NS / 2 - 1]) + fast_sqrt(v[NS / 2]));
+}
+
+template <int NS>
+__device__ __forceinline__ void simmodel_large(const float* __restrict__ vchan, size_t vrow, const int* __restrict__ list,
+                                               int n, float* __restrict__ out, int t) {
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) out[t + 128 * i] = gather_median_large<NS>(vchan, vrow, list, n, t + 128 * i);
+    if (t == 0) out[XPITCH] = gather_median_large<NS>(vchan, vrow, list, n, XPITCH);
+}
+
+// k_simmodel_large: lists of 33..128 similar frames.  One CTA of 128 threads per (frame, channel); a
+// thread gathers the n squared magnitudes of a bin (4-byte coalesced loads from Vsq) into registers and
+// runs a pruned selection network -- no shared-memory tile, no data-dependent control flow.
+__global__ void __launch_bounds__(128, 3)
+k_simmodel_large(const float* __restrict__ Vsq, int T, int nch, const int* __restrict__ idx, const int* __restrict__ cnt,
+                 int number, int first_frame, float* __restrict__ model) {
+    __shared__ int s_list[128];
+    const int j = blockIdx.x + first_frame;
+    const int item = blockIdx.y / nch, c = blockIdx.y - item * nch;
+    const int t = threadIdx.x;
+    const int n = cnt[(size_t)item * T + j];
+    if (n <= 32 || n > 128) return;  // k_simmodel handles those
+    if (t < n) s_list[t] = idx[((size_t)item * T + j) * (size_t)number + t];
+    __syncthreads();
+    const float* __restrict__ vchan = Vsq + ((size_t)item * T * nch + c) * PPITCH;
+    const size_t vrow = (size_t)nch * PPITCH;
+    float* __restrict__ out = model + (((size_t)item * nch + c) * (size_t)T + j) * PPITCH;
+    if (n <= 48) simmodel_large<48>(vchan, vrow, s_list, n, out, t);
+    else if (n <= 64) simmodel_large<64>(vchan, vrow, s_list, n, out, t);
+    else if (n <= 100) simmodel_large<100>(vchan, vrow, s_list, n, out, t);
+    else simmodel_large<128>(vchan, vrow, s_list, n, out, t);
+}
+
 __global__ void __launch_bounds__(SIMMODEL_THREADS)
-k_simmodel(const float2* __restrict__ X, int T, int nch, const int* __restrict__ idx, const int* __restrict__ cnt,
-           int number, int first_frame, float* __restrict__ model) {
+k_simmodel(const float2* __restrict__ X, const float* __restrict__ Vsq, int T, int nch, const int* __restrict__ idx,
+           const int* __restrict__ cnt, int number, int first_frame, float* __restrict__ model) {
     extern __shared__ __align__(16) unsigned char smem[];
     int* s_list = reinterpret_cast<int*>(smem);                              // [number]
     float* s_tile = reinterpret_cast<float*>(s_list + ((number + 3) & ~3));  // [n][256] when n > 32
@@ -459,6 +604,7 @@ k_simmodel(const float2* __restrict__ X, int T, int nch, const int* __restrict__
         for (int k = t; k <= XPITCH; k += SIMMODEL_THREADS) out[k] = nanf("");
         return;
     }
+    if (n > 32 && n <= 128) return;  // k_simmodel_large
     if (n <= 32) {
         // short lists: register selection networks on bin pairs, 128 threads x 4 passes
         if (t < 128) {
@@ -474,37 +620,43 @@ k_simmodel(const float2* __restrict__ X, int T, int nch, const int* __restrict__
         }
         return;
     }
-    // long lists: one bin per thread, 4 passes of 256 bins; squared magnitudes staged in the thread's
-    // own shared-memory column (bank = lane: conflict free), 8 gathers in flight per thread
+    // long lists: 4 passes of 256 bins.  The CTA gathers the [n][256] tile of squared magnitudes with
+    // 16-byte loads (4 rows per sweep, 8 sweeps in flight per thread), then every thread selects the
+    // median of its own column (bank = lane: conflict free) by quickselect.
+    const float* __restrict__ vchan = Vsq + ((size_t)item * T * nch + c) * PPITCH;
+    const size_t vrow = (size_t)nch * PPITCH;
+    const int sub = t >> 6, quad = (t & 63) * 4;  // this thread gathers row (4 s' + sub), bins quad..quad+3
     for (int pass = 0; pass < 4; ++pass) {
-        const int k = t + 256 * pass;
-        for (int s0 = 0; s0 < n; s0 += 8) {
-            float2 x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = __ldg(chan + (size_t)s_list[min(s0 + u, n - 1)] * row + k);
+        const int k0 = 256 * pass;
+        for (int s0 = 0; s0 < n; s0 += 32) {
+            float4 x[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int s = s0 + u;
-                if (s < n)
-                    s_tile[s * 256 + t] = (k == 0) ? __fmul_rn(x[u].x, x[u].x) : __fmaf_rn(x[u].x, x[u].x, __fmul_rn(x[u].y, x[u].y));
+                const int s = min(s0 + 4 * u + sub, n - 1);
+                x[u] = __ldg(reinterpret_cast<const float4*>(vchan + (size_t)s_list[s] * vrow + k0 + quad));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s = s0 + 4 * u + sub;
+                if (s < n) *reinterpret_cast<float4*>(s_tile + s * 256 + quad) = x[u];
             }
         }
-        out[k] = tile_median(s_tile, n, 256, t);  // the column is private: no barrier needed
+        __syncthreads();
+        out[k0 + t] = tile_median(s_tile, n, 256, t);
+        __syncthreads();
     }
     if (t == 0) {
-        // Nyquist rides in bin 0's imaginary slot
-        for (int s = 0; s < n; ++s) {
-            const float y = __ldg(&chan[(size_t)s_list[s] * row]).y;
-            s_tile[s * 256] = __fmul_rn(y, y);
-        }
+        // Nyquist^2 sits at bin 1024 of the Vsq rows
+        for (int s = 0; s < n; ++s) s_tile[s * 256] = __ldg(vchan + (size_t)s_list[s] * vrow + XPITCH);
         out[XPITCH] = tile_median(s_tile, n, 256, 0);
     }
 }
 
-int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* idx, const int* cnt,
-                    int number, int first_frame, float* model) {
+int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_items, int T, int nch, const int* idx,
+                    const int* cnt, int number, int first_frame, float* model) {
     const size_t smem = (size_t)((number + 3) & ~3) * 4 + (number > 32 ? (size_t)number * 256 * 4 : 0);
     if (smem > 220 * 1024) return -1;
+    if (number > 32 && !Vsq) return -2;
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
         cudaFuncSetAttribute(k_simmodel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -512,7 +664,8 @@ int launch_simmodel(cudaStream_t st, const float2* X, int n_items, int T, int nc
     }
     if (T <= first_frame) return 0;
     dim3 grid(T - first_frame, n_items * nch);
-    k_simmodel<<<grid, SIMMODEL_THREADS, smem, st>>>(X, T, nch, idx, cnt, number, first_frame, model);
+    k_simmodel<<<grid, SIMMODEL_THREADS, smem, st>>>(X, Vsq, T, nch, idx, cnt, number, first_frame, model);
+    if (number > 32) k_simmodel_large<<<grid, 128, 0, st>>>(Vsq, T, nch, idx, cnt, number, first_frame, model);
     return 0;
 }
 

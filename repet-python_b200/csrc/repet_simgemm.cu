@@ -25,20 +25,30 @@ namespace repet {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;  // BK floats = 128 bytes = one swizzle atom
-constexpr int STAGES = 4;
-constexpr int KBLOCKS = KPAD / BK;          // 33
-constexpr int A_BYTES = BM * BK * 4;        // 16 KB
-constexpr int B_BYTES = BN * BK * 4;        // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128, BK = 32;  // BK floats = 128 bytes = one swizzle atom
+constexpr int KBLOCKS = KPAD / BK;  // 33
+constexpr int A_BYTES = BM * BK * 4;  // 16 KB
 constexpr int EPI_PITCH = 33;
 constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
 constexpr int GEMM_THREADS = 192;
-constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 512;
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10) [10,13), K-major both,
-// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// Two configurations:
+//   single pass  BN 256, 4 stages of (A 16 KB + B 32 KB): S~ = hi hi^T, |error| <= ~1e-3
+//   split pass   BN 128, 3 stages of (A_hi, A_lo, B_hi, B_lo: 4 x 16 KB): A = hi + lo with both parts
+//                TF32, S~ = hi hi^T + hi lo^T + lo hi^T accumulated in the same TMEM tile ("3xTF32",
+//                fp32-class accuracy for 3x the MMAs)
+template <int BN, bool SPLIT3>
+struct GemmCfg {
+    static constexpr int STAGES = SPLIT3 ? 3 : 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators (power of two: 256 or 512)
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10) [10,13), K-major
+    // both, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+    static constexpr uint32_t IDESC =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,12 +90,13 @@ __device__ __forceinline__ uint64_t umma_desc(const void* tile) {
     return (uint64_t)((smem_u32(tile) & 0x3ffffu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(IDESC), "r"(accumulate)
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -105,9 +116,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int T, int n_items,
+k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, int T, int n_items,
           float* __restrict__ S) {
+    using Cfg = GemmCfg<BN, SPLIT3>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int B_BYTES = Cfg::B_BYTES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = Cfg::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* tiles = smem;                                        // STAGES x (A | B), each 1024-aligned
@@ -159,6 +177,10 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
                     tma_load_2d(a_dst, &map_a, kb * BK, item * T + m0, &full[s]);
                     tma_load_2d(a_dst + A_BYTES, &map_b, kb * BK, item * T + n0, &full[s]);
+                    if (SPLIT3) {
+                        tma_load_2d(a_dst + A_BYTES + B_BYTES, &map_a_lo, kb * BK, item * T + m0, &full[s]);
+                        tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * BK, item * T + n0, &full[s]);
+                    }
                 }
             }
         }
@@ -179,7 +201,16 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     const uint64_t da = umma_desc(a_tile), db = umma_desc(a_tile + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k)  // 8 floats = 32 bytes = 2 descriptor units per K step
-                        umma_tf32(tmem_d, da + 2 * k, db + 2 * k, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_d, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
+                    if (SPLIT3) {
+                        const uint64_t da_lo = umma_desc(a_tile + A_BYTES + B_BYTES);
+                        const uint64_t db_lo = umma_desc(a_tile + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            umma_tf32(tmem_d, da + 2 * k, db_lo + 2 * k, Cfg::IDESC, 1u);  // hi lo^T
+                            umma_tf32(tmem_d, da_lo + 2 * k, db + 2 * k, Cfg::IDESC, 1u);  // lo hi^T
+                        }
+                    }
                     umma_commit(&empty[s]);  // frees the stage once the MMAs have read it
                 }
                 umma_commit(&acc_full[acc]);  // accumulator complete
@@ -255,23 +286,34 @@ bool make_map(CUtensorMap* map, const float* base, size_t rows, int box_rows) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace
-
-// S[item] = An32[item] An32[item]^T for n_items stacked [T][KPAD] operands.  Returns 0 on success.
-int launch_selfsim_tc(cudaStream_t st, const float* An32, int n_items, int T, float* S, int sm_count) {
-    CUtensorMap map_a, map_b;
+template <int BN, bool SPLIT3>
+int launch_gemm(cudaStream_t st, const float* hi, const float* lo, int n_items, int T, float* S, int sm_count) {
+    using Cfg = GemmCfg<BN, SPLIT3>;
+    CUtensorMap map_a, map_b, map_a_lo, map_b_lo;
     const size_t rows = (size_t)n_items * T;
-    if (!make_map(&map_a, An32, rows, BM) || !make_map(&map_b, An32, rows, BN)) return -1;
+    if (!make_map(&map_a, hi, rows, BM) || !make_map(&map_b, hi, rows, BN)) return -1;
+    if (!make_map(&map_a_lo, SPLIT3 ? lo : hi, rows, BM) || !make_map(&map_b_lo, SPLIT3 ? lo : hi, rows, BN)) return -1;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_simgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(k_simgemm<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) !=
+            cudaSuccess)
+            return -2;
         configured = true;
     }
     const int mt = (T + BM - 1) / BM, nt = (T + BN - 1) / BN;
     const int tiles_total = n_items * mt * nt;
     const int grid = std::max(1, std::min(tiles_total, sm_count));
-    k_simgemm<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_b, T, n_items, S);
+    k_simgemm<BN, SPLIT3><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(map_a, map_b, map_a_lo, map_b_lo, T, n_items, S);
     return 0;
+}
+
+}  // namespace
+
+// S[item] = A[item] A[item]^T for n_items stacked [T][KPAD] operands.  `lo` = nullptr: single TF32 pass
+// on `hi`; otherwise the 3xTF32 split product of hi + lo.  Returns 0 on success.
+int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_items, int T, float* S, int sm_count) {
+    if (lo) return launch_gemm<128, true>(st, hi, lo, n_items, T, S, sm_count);
+    return launch_gemm<256, false>(st, hi, nullptr, n_items, T, S, sm_count);
 }
 
 }  // namespace repet

@@ -38,10 +38,11 @@ def _assert_lists(lists, counts_ref, flat_ref, what, first=0):
     assert np.array_equal(flat, flat_ref), "%s: %d of %d indices differ" % (what, int(np.sum(flat != flat_ref)), len(flat_ref))
 
 
-@pytest.mark.parametrize("seconds,tensor_core", [(3.0, 1), (13.7, 1), (13.7, 0), (31.0, 1)])
+@pytest.mark.parametrize("seconds,tensor_core", [(3.0, 2), (13.7, 2), (13.7, 1), (13.7, 0), (31.0, 2), (31.0, 1)])
 def test_selfsimilarity_fast_pass(repet, seconds, tensor_core):
     """The tcgen05 TF32 product (and the fp32 cross-check kernel) against the float64 reference
-    formula: within the bound `tau` the drivers certify against (1.5e-3 / 1e-4)."""
+    formula: within the bound `tau` the drivers certify against (3xTF32 split 1e-4, single TF32
+    1.5e-3, fp32 CUDA cores 1e-4); the split pass is expected to be ~100x inside its bound."""
     x = repet_synth.make_clip(31, int(seconds * FS)).astype(np.float64)
     N, w, H = oracle.stft_parameters(FS)
     V = np.mean(np.stack([np.abs(oracle.stft(x[c], w, H)[: N // 2 + 1]) for c in range(2)], axis=2), axis=2)
@@ -50,11 +51,13 @@ def test_selfsimilarity_fast_pass(repet, seconds, tensor_core):
     try:
         S = repet._host.selfsimilarity(V)
     finally:
-        repet._host.set_tuning(simgemm_tc=1)
+        repet._host.set_tuning(simgemm_tc=2)
     assert S.shape == S_ref.shape
     err = float(np.max(np.abs(S - S_ref)))
-    assert err <= (1.5e-3 if tensor_core else 1e-4), err
-    assert np.array_equal(S, S.T)  # both passes are bitwise symmetric
+    print("fast pass %d, T=%d: max |S~ - S| = %.3e" % (tensor_core, S.shape[0], err))
+    assert err <= {2: 5e-5, 1: 1.5e-3, 0: 1e-4}[tensor_core], err
+    if tensor_core < 2:
+        assert np.array_equal(S, S.T)  # single products are bitwise symmetric
 
 
 def test_sim_lists_do_not_depend_on_the_fast_pass(repet):
@@ -62,13 +65,14 @@ def test_sim_lists_do_not_depend_on_the_fast_pass(repet):
     certification the lists must be identical."""
     x = make_golden.case_input(make_golden.DRIVER_CASES["synth_12s"])
     y_tc, lists_tc = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
-    repet._host.set_tuning(simgemm_tc=0)
-    try:
-        y_simt, lists_simt = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
-    finally:
-        repet._host.set_tuning(simgemm_tc=1)
-    assert all(np.array_equal(a, b) for a, b in zip(lists_tc, lists_simt))
-    assert np.array_equal(y_tc, y_simt)
+    for mode in (1, 0):
+        repet._host.set_tuning(simgemm_tc=mode)
+        try:
+            y_other, lists_other = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+        finally:
+            repet._host.set_tuning(simgemm_tc=2)
+        assert all(np.array_equal(a, b) for a, b in zip(lists_tc, lists_other)), mode
+        assert np.array_equal(y_tc, y_other), mode
 
 
 @pytest.mark.parametrize("case", ["wav_5s", "synth_12s", "synth_mono_8s", "wav_full"])
