@@ -249,12 +249,13 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
+def ncu_traffic(kernel, clips_per_launch):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel`, scaled from the committed
+    ncu --set full capture (profiles/traffic.json holds bytes per clip), or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get(kernel)
+            return json.load(f)[kernel]["dram_bytes_per_clip"] * clips_per_launch
     except Exception:
         return None
 
@@ -392,7 +393,8 @@ def run_b200_arm(args, rank, local_rank, world):
         if dominant:
             d = kernels[dominant]
             roofline = {"bound": "hbm", "kernel": dominant, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": d["frac"], "traffic": ncu_traffic(dominant), "peak_source": peak_source,
+                        "frac": d["frac"],
+                        "traffic": ncu_traffic(dominant, B * args.steps / max(1, d["launches"])), "peak_source": peak_source,
                         "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
                         "avg_launch_ms": d["ms_total"] / max(1, d["launches"]), "kernels": kernels,
                         "whole_path_algorithmic_gbs": (2 * audio_bytes + 2 * x_bytes + 2 * p_bytes) * B * args.steps / (elapsed_ms / 1e3) / 1e9}

@@ -415,7 +415,9 @@ int run_extended(repet_handle* h, const Plan& plan, const float* audio, int n_cl
 int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_clips, float* out, int32_t* ints,
                  unsigned char* ws, size_t ws_bytes) {
     const int nch = plan.nch, T = plan.T;
-    const int G = (int)std::min<size_t>(std::min<size_t>((size_t)n_clips, MAX_ITEMS_PER_LAUNCH / 2),
+    // grid.y carries clips x beat segments in k_beat: keep it below 65535
+    const size_t grid_cap = std::max<size_t>(1, 60000 / (size_t)std::max(1, plan.n_beat_seg));
+    const int G = (int)std::min<size_t>(std::min<size_t>((size_t)n_clips, std::min<size_t>(MAX_ITEMS_PER_LAUNCH / 2, grid_cap)),
                                         std::max<size_t>(1, ws_bytes / plan.bytes_per_clip));
     const float scale = (float)(1.0 / ((double)WIN_N * plan.p.cola_gain));
     cudaStream_t st = h->stream;

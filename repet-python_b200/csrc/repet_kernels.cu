@@ -801,8 +801,8 @@ __global__ void __launch_bounds__(128)
 k_mask_only(const float2* __restrict__ X, int T, int nch, const int* __restrict__ period, int pmax,
             const float* __restrict__ model, float* __restrict__ mask_out) {
     const int item = blockIdx.z / nch, c = blockIdx.z - item * nch;
-    const int j = blockIdx.y;
-    const int k = blockIdx.x * 128 + threadIdx.x;
+    const int j = blockIdx.x;  // frames on grid.x: there can be more than 65535 of them
+    const int k = blockIdx.y * 128 + threadIdx.x;
     if (k > XPITCH) return;
     const int p = period ? period[item] : pmax;
     const float2* __restrict__ row = X + ((size_t)item * T + j) * (size_t)(nch * XPITCH) + (size_t)c * XPITCH;
@@ -812,7 +812,7 @@ k_mask_only(const float2* __restrict__ X, int T, int nch, const int* __restrict_
 
 void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
                       const float* model, float* mask_out) {
-    dim3 grid(9, T, n_items * nch);
+    dim3 grid(T, 9, n_items * nch);
     k_mask_only<<<grid, 128, 0, st>>>(X, T, nch, period, pmax, model, mask_out);
 }
 

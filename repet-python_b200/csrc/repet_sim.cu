@@ -515,8 +515,8 @@ constexpr int SIMMODEL_THREADS = 256;
 // Long similar-frame lists gather these 4-byte values instead of the 8-byte spectra.
 __global__ void __launch_bounds__(256)
 k_sqmag(const float2* __restrict__ X, long long n_rows, float* __restrict__ Vsq) {
-    const long long row = blockIdx.y;
-    const int k = blockIdx.x * 256 + threadIdx.x;
+    const long long row = blockIdx.x;  // rows on grid.x: there can be more than 65535 of them
+    const int k = blockIdx.y * 256 + threadIdx.x;
     if (row >= n_rows || k > XPITCH) return;
     const float2* __restrict__ x = X + row * XPITCH;
     float v;
@@ -533,7 +533,7 @@ k_sqmag(const float2* __restrict__ X, long long n_rows, float* __restrict__ Vsq)
 }
 
 void launch_sqmag(cudaStream_t st, const float2* X, long long n_rows, float* Vsq) {
-    dim3 grid(5, (unsigned)n_rows);
+    dim3 grid((unsigned)n_rows, 5);
     k_sqmag<<<grid, 256, 0, st>>>(X, n_rows, Vsq);
 }
 
