@@ -105,6 +105,10 @@ int repet_original_batch_dev(repet_handle* h, const float* audio, int n_clips, i
 /* Same with HOST buffers (pinned memory recommended); copies are chunked and overlapped. */
 int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                          const repet_params* p, float* background, int32_t* periods_host);
+/* Same with int16 PCM input in WAV order [n_clips][n_samples][n_channels] (what wavread reads before it
+ * normalises by 2^15, repet.py:926-929): half the host-to-device bytes; output fp32 planar. */
+int repet_original_batch_pcm16(repet_handle* h, const int16_t* audio, int n_clips, int n_channels, int64_t n_samples,
+                               const repet_params* p, float* background, int32_t* periods_host);
 /* The reference's exact calling convention for one clip: float64 (n_samples, n_channels)
  * in and out, host pointers (repet.py:73-77). */
 int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels,

@@ -508,8 +508,13 @@ int batch_dev(repet_handle* h, int kind, const float* audio, int n_clips, int nc
     return REPET_OK;
 }
 
-int batch_host(repet_handle* h, int kind, const float* audio, int n_clips, int nch, int64_t S, const repet_params* p,
-               float* background, int32_t* ints_host) {
+// `pcm16`: the input is int16 PCM in WAV order [clip][sample][channel] (2 bytes per sample over PCIe
+// instead of 4); it is normalised by 2^15 as repet.wavread does (repet.py:929) and made planar on the
+// device.
+int batch_host(repet_handle* h, int kind, const void* audio_any, bool pcm16, int n_clips, int nch, int64_t S,
+               const repet_params* p, float* background, int32_t* ints_host) {
+    const float* audio = static_cast<const float*>(audio_any);
+    const int16_t* audio_pcm = static_cast<const int16_t*>(audio_any);
     int rc = check_common(h, p, nch);
     if (rc) return rc;
     if (!audio || !background || n_clips < 0 || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
@@ -525,25 +530,37 @@ int batch_host(repet_handle* h, int kind, const float* audio, int n_clips, int n
     const size_t slot_bytes = align_up((size_t)Gc * clip_bytes);
     const size_t ints_bytes = align_up((size_t)n_clips * plan.ints_per_clip * sizeof(int32_t));
     const size_t ws_bytes = (size_t)Gw * plan.bytes_per_clip;
-    if ((rc = ensure_arena(h, ints_bytes + 4 * slot_bytes + ws_bytes))) return rc;
+    const size_t pcm_bytes = pcm16 ? slot_bytes : 0;  // one fp32 conversion target (the PCM slots are half size)
+    if ((rc = ensure_arena(h, ints_bytes + 4 * slot_bytes + pcm_bytes + ws_bytes))) return rc;
     int32_t* ints = reinterpret_cast<int32_t*>(h->arena);
     float* in_slot[2] = {reinterpret_cast<float*>(h->arena + ints_bytes),
                          reinterpret_cast<float*>(h->arena + ints_bytes + slot_bytes)};
     float* out_slot[2] = {reinterpret_cast<float*>(h->arena + ints_bytes + 2 * slot_bytes),
                           reinterpret_cast<float*>(h->arena + ints_bytes + 3 * slot_bytes)};
-    unsigned char* ws = h->arena + ints_bytes + 4 * slot_bytes;
+    float* converted = reinterpret_cast<float*>(h->arena + ints_bytes + 4 * slot_bytes);
+    unsigned char* ws = h->arena + ints_bytes + 4 * slot_bytes + pcm_bytes;
     CU(cudaStreamSynchronize(h->stream));  // the arena must be idle before the copy streams touch it
     int n_chunks = 0;
     for (int first = 0; first < n_clips; first += Gc, ++n_chunks) {
         const int s = n_chunks & 1;
         const int g = std::min(Gc, n_clips - first);
         if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_compute[s], 0));  // slot's input consumed
-        CU(cudaMemcpyAsync(in_slot[s], audio + (size_t)first * clip_elems, (size_t)g * clip_bytes, cudaMemcpyHostToDevice,
-                           h->h2d_stream));
+        if (pcm16)
+            CU(cudaMemcpyAsync(in_slot[s], audio_pcm + (size_t)first * clip_elems, (size_t)g * clip_elems * sizeof(int16_t),
+                               cudaMemcpyHostToDevice, h->h2d_stream));
+        else
+            CU(cudaMemcpyAsync(in_slot[s], audio + (size_t)first * clip_elems, (size_t)g * clip_bytes,
+                               cudaMemcpyHostToDevice, h->h2d_stream));
         CU(cudaEventRecord(h->ev_h2d[s], h->h2d_stream));
         CU(cudaStreamWaitEvent(h->stream, h->ev_h2d[s], 0));
         if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_d2h[s], 0));  // slot's output drained
-        rc = run_plan(h, plan, in_slot[s], g, out_slot[s], ints + (size_t)first * plan.ints_per_clip, ws, ws_bytes);
+        const float* chunk_in = in_slot[s];
+        if (pcm16) {
+            Timed timed(h, REPET_K_CONVERT);
+            launch_pcm16_to_planar(h->stream, reinterpret_cast<const int16_t*>(in_slot[s]), g, S, nch, converted);
+            chunk_in = converted;
+        }
+        rc = run_plan(h, plan, chunk_in, g, out_slot[s], ints + (size_t)first * plan.ints_per_clip, ws, ws_bytes);
         if (rc) return rc;
         CU(cudaEventRecord(h->ev_compute[s], h->stream));
         CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute[s], 0));
@@ -609,11 +626,16 @@ int repet_original_batch_dev(repet_handle* h, const float* audio, int n_clips, i
 }
 int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                          const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_ORIGINAL, audio, n_clips, n_channels, n_samples, p, background, periods_host);
+    return batch_host(h, KIND_ORIGINAL, audio, false, n_clips, n_channels, n_samples, p, background, periods_host);
 }
 int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                        double* background, int32_t* period_host) {
     return single_f64(h, KIND_ORIGINAL, audio, n_samples, n_channels, p, background, period_host, 1);
+}
+
+int repet_original_batch_pcm16(repet_handle* h, const int16_t* audio, int n_clips, int n_channels, int64_t n_samples,
+                               const repet_params* p, float* background, int32_t* periods_host) {
+    return batch_host(h, KIND_ORIGINAL, audio, true, n_clips, n_channels, n_samples, p, background, periods_host);
 }
 
 // ---- repet.extended (repet.py:205-419) -----------------------------------------------------
@@ -628,7 +650,7 @@ int repet_extended_batch_dev(repet_handle* h, const float* audio, int n_clips, i
 }
 int repet_extended_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                          const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_EXTENDED, audio, n_clips, n_channels, n_samples, p, background, periods_host);
+    return batch_host(h, KIND_EXTENDED, audio, false, n_clips, n_channels, n_samples, p, background, periods_host);
 }
 int repet_extended_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                        double* background, int32_t* periods_host, int periods_capacity) {
@@ -642,7 +664,7 @@ int repet_adaptive_batch_dev(repet_handle* h, const float* audio, int n_clips, i
 }
 int repet_adaptive_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                          const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_ADAPTIVE, audio, n_clips, n_channels, n_samples, p, background, periods_host);
+    return batch_host(h, KIND_ADAPTIVE, audio, false, n_clips, n_channels, n_samples, p, background, periods_host);
 }
 int repet_adaptive_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                        double* background, int32_t* periods_host, int periods_capacity) {
@@ -656,7 +678,7 @@ int repet_sim_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_
 }
 int repet_sim_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                     const repet_params* p, float* background, int32_t* lists_host) {
-    return batch_host(h, KIND_SIM, audio, n_clips, n_channels, n_samples, p, background, lists_host);
+    return batch_host(h, KIND_SIM, audio, false, n_clips, n_channels, n_samples, p, background, lists_host);
 }
 int repet_sim_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                   double* background, int32_t* lists_host, int lists_capacity) {
@@ -674,7 +696,7 @@ int repet_simonline_batch_dev(repet_handle* h, const float* audio, int n_clips, 
 }
 int repet_simonline_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                           const repet_params* p, float* background, int32_t* lists_host) {
-    return batch_host(h, KIND_SIMONLINE, audio, n_clips, n_channels, n_samples, p, background, lists_host);
+    return batch_host(h, KIND_SIMONLINE, audio, false, n_clips, n_channels, n_samples, p, background, lists_host);
 }
 int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                         double* background, int32_t* lists_host, int lists_capacity) {

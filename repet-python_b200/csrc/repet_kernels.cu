@@ -993,6 +993,19 @@ __global__ void k_planar_to_f64(const float* __restrict__ in, long long S, int C
     const int c = (int)(n - s * C);
     out[n] = (double)in[(long long)c * S + s];
 }
+// int16 PCM in WAV order [clip][sample][channel] -> fp32 planar [clip][channel][sample] / 2^15 (repet.py:929)
+__global__ void k_pcm16_to_planar(const int16_t* __restrict__ in, long long S, int C, float* __restrict__ out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const long long clip = blockIdx.y;
+    const int16_t* __restrict__ src = in + (clip * S + s) * C;
+    for (int c = 0; c < C; ++c) out[(clip * C + c) * S + s] = (float)src[c] * (1.0f / 32768.0f);
+}
+void launch_pcm16_to_planar(cudaStream_t st, const int16_t* in, int n_clips, long long S, int C, float* out) {
+    dim3 grid((unsigned)((S + 255) / 256), n_clips);
+    k_pcm16_to_planar<<<grid, 256, 0, st>>>(in, S, C, out);
+}
+
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out) {
     const long long n = S * C;
     k_f64_to_planar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, S, C, out);

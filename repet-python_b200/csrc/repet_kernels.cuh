@@ -120,6 +120,7 @@ int launch_localmaxima64(cudaStream_t st, const double* data, int n, int n_colum
                          int* idx_out, int* cnt_out, double* val_out);
 
 // layout converters for the float64 (S, C) NumPy convention of the reference API
+void launch_pcm16_to_planar(cudaStream_t st, const int16_t* in, int n_clips, long long S, int C, float* out);
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out);
 void launch_planar_to_f64_interleaved(cudaStream_t st, const float* in, long long S, int C, double* out);
 

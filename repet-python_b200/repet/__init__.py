@@ -98,6 +98,12 @@ def original_batch(audio_signals, sampling_frequency):
     return _host.original_batch(audio_signals, sampling_frequency, _tunables())
 
 
+def original_batch_pcm16(pcm_signals, sampling_frequency):
+    """The original REPET over int16 PCM clips as stored in WAVE files: (number_clips, number_samples,
+    number_channels) int16 -> float32 backgrounds (number_clips, number_channels, number_samples), periods."""
+    return _host.original_batch_pcm16(pcm_signals, sampling_frequency, _tunables())
+
+
 def extended_batch(audio_signals, sampling_frequency):
     """REPET extended over a batch (see original_batch); periods: int32 (number_clips, number_segments)."""
     return _host.driver_batch("extended", audio_signals, sampling_frequency, _tunables())

@@ -72,6 +72,7 @@ SIGNATURES = {
     "repet_kernel_name": (ctypes.c_char_p, [_c_int]),
     "repet_original_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_original_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_original_batch_pcm16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
     "repet_original_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp]),
     "repet_extended_segments": (_c_int, [_pp, _c_i64]),
     "repet_extended_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
@@ -683,3 +684,24 @@ def acorr(data_matrix, handle=None):
     out = np.empty((rows, columns), dtype=np.float64)
     handle.check(handle.lib.repet_acorr(handle.h, _ptr(data), rows, columns, _ptr(out)))
     return out
+
+
+def original_batch_pcm16(pcm, sampling_frequency, tunables, handle=None):
+    """`original` over int16 PCM clips in WAV order: pcm (B, S, C) int16 -> (background (B, C, S) float32,
+    periods (B,) int32).  The samples are normalised by 2^15 on the device, as repet.wavread does."""
+    handle = handle or get_handle()
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    if pcm.ndim != 3:
+        raise ValueError("pcm must have shape (clips, samples, channels)")
+    number_clips, number_samples, number_channels = pcm.shape
+    params, _ = derive_params(sampling_frequency, tunables)
+    handle.ensure_window(params.window_length)
+    background = np.empty((number_clips, number_channels, number_samples), dtype=np.float32)
+    periods = np.zeros(number_clips, dtype=np.int32)
+    handle.check(
+        handle.lib.repet_original_batch_pcm16(
+            handle.h, _ptr(pcm), number_clips, number_channels, number_samples, ctypes.byref(params), _ptr(background),
+            _ptr(periods),
+        )
+    )
+    return background, periods

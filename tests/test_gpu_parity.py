@@ -286,3 +286,13 @@ def test_original_long_clip_blocked_beat_transform(repet):
     y2_ref, det2 = oracle.original(x, FS, return_details=True, period_range=(0.5, 2))
     assert period2 == det2["period"] and -(-3877 // period2) > 32
     _assert_signal(y2, y2_ref, "original, 90 s, short periods")
+
+
+def test_original_batch_pcm16_matches_float_path(repet, wav_pcm):
+    """int16 PCM in WAV order, normalised on the device exactly as repet.wavread does (x / 2^15)."""
+    pcm = np.stack([wav_pcm[0 : 6 * FS], wav_pcm[8 * FS : 14 * FS]])  # (2, S, 2) int16
+    background, periods = repet.original_batch_pcm16(pcm, FS)
+    audio = np.ascontiguousarray(np.transpose(pcm / 32768.0, (0, 2, 1)), dtype=np.float32)
+    ref_background, ref_periods = repet.original_batch(audio, FS)
+    assert np.array_equal(periods, ref_periods)
+    assert np.array_equal(background, ref_background)  # int16 / 2^15 is exact in fp32
