@@ -51,7 +51,8 @@ typedef struct repet_params {
     int32_t similarity_distance; /* frames                               repet.py:670 */
     int32_t similarity_number;   /*                                      repet.py:60  */
     int32_t buffer_frames;    /* simonline ring length in frames         repet.py:787 */
-    int32_t reserved0;
+    int32_t online_frame_base; /* simonline on a window of a longer stream: absolute index of the window's
+                                * first frame (ring slot = absolute frame mod buffer_frames, quirk Q6); 0 otherwise */
     double similarity_threshold; /*                                      repet.py:58  */
     double cola_gain;         /* sum(window[0:N:H])                      repet.py:1103 */
 } repet_params;

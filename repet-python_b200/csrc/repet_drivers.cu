@@ -242,8 +242,10 @@ int make_plan(repet_handle* h, int kind, const repet_params* p, int nch, int64_t
         if (kind == KIND_SIMONLINE) {
             const int B = p->buffer_frames;
             if (B < 1) return fail(h, REPET_E_INVALID_ARG, "buffer_length must cover at least one frame");
-            // the reference's warm-up loop multiplies a truncated slice by the window (repet.py:801-804)
-            if (S < WIN_N || (int64_t)(B - 2) * HOP + WIN_N > S)
+            if (p->online_frame_base < 0) return fail(h, REPET_E_INVALID_ARG, "online_frame_base must not be negative");
+            // the reference's warm-up loop multiplies a truncated slice by the window (repet.py:801-804);
+            // a window of a longer stream (online_frame_base > 0) has had its warm-up earlier
+            if (S < WIN_N || (p->online_frame_base == 0 && (int64_t)(B - 2) * HOP + WIN_N > S))
                 return fail(h, REPET_E_INVALID_ARG,
                             "operands could not be broadcast together (signal shorter than the buffer)");
             T = (int)((S - WIN_N + HOP - 1) / HOP) + 1;  // repet.py:781, frames are not centred
@@ -308,7 +310,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         geom.first_offset = (long long)clip0 * geom.clip_stride;
         if (online) {
             geom.frame_shift = 1;
-            geom.first_frame = plan.buffer_frames - 1;
+            geom.first_frame = std::max(0, plan.buffer_frames - 1 - plan.p.online_frame_base);
         }
         const int K = pick_frames_per_cta(h, (long long)g * T);
         {
@@ -322,8 +324,8 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         CU(cudaMemsetAsync(cnt, 0, (size_t)g * T * sizeof(int32_t), st));
         if (online) {
             Timed timed(h, REPET_K_TOPK);
-            launch_online_select(st, An64, g, T, plan.buffer_frames, plan.p.similarity_threshold, plan.distance,
-                                 plan.number, idx, cnt);
+            launch_online_select(st, An64, g, T, plan.buffer_frames, plan.p.online_frame_base,
+                                 plan.p.similarity_threshold, plan.distance, plan.number, idx, cnt);
         } else {
             {
                 Timed timed(h, REPET_K_SIMGEMM);

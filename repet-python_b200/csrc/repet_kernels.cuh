@@ -107,8 +107,8 @@ int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_i
 void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
                 int number, int* idx_out, int* cnt_out, int* overflow);
-void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, double thr, int d, int number,
-                          int* idx_out, int* cnt_out);
+void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
+                          int d, int number, int* idx_out, int* cnt_out);
 void launch_sqmag(cudaStream_t st, const float2* X, long long n_rows, float* Vsq);
 // Vsq (squared magnitudes [item][T][nch][PPITCH]) is required when number > 32
 int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_items, int T, int nch, const int* idx,

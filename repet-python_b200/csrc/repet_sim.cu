@@ -341,25 +341,30 @@ int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items
 constexpr int ONLINE_FB = 8;  // target frames per CTA
 
 __global__ void __launch_bounds__(256)
-k_online_select(const double* __restrict__ An64, int T, int B, double thr, int d, int number, int* __restrict__ idx_out,
-                int* __restrict__ cnt_out) {
+k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, double thr, int d, int number,
+                int* __restrict__ idx_out, int* __restrict__ cnt_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* s_tgt = reinterpret_cast<double*>(smem);          // [ONLINE_FB][APITCH64]  target frames
     double* s_sim = s_tgt + ONLINE_FB * APITCH64;             // [ONLINE_FB][B]         similarity by ring slot
     unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_sim + ONLINE_FB * B);  // [ONLINE_FB][B]
     __shared__ int s_kept[ONLINE_FB];
     const int item = blockIdx.y;
-    const int j_first = blockIdx.x * ONLINE_FB + (B - 1);
+    // rows are frames frame_base .. frame_base + T - 1 of the stream; the first synthesised row is the
+    // one whose absolute index is B - 1
+    const int row_first = max(0, B - 1 - frame_base);
+    const int j_first = blockIdx.x * ONLINE_FB + row_first;
     const int nf = min(ONLINE_FB, T - j_first);  // target frames of this CTA
     if (nf <= 0) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const double* __restrict__ A = An64 + (size_t)item * T * APITCH64;
     if (t < ONLINE_FB) s_kept[t] = 0;
     for (int k = t; k < nf * APITCH64; k += blockDim.x) s_tgt[k] = A[(size_t)j_first * APITCH64 + k];
+    // slots whose frame lies before the window (a stream window with partial history) can never be maxima
+    for (int e = t; e < nf * B; e += blockDim.x) s_sim[e] = -INFINITY;
     __syncthreads();
     // Frame u sits in ring slot u mod B.  Every buffer frame of the block's targets is read ONCE and
     // dotted (exact float64) against all the targets it belongs to: u in [j-B+1, j].
-    const int u_lo = j_first - (B - 1), u_hi = j_first + nf - 1;
+    const int u_lo = max(0, j_first - (B - 1)), u_hi = j_first + nf - 1;
     for (int u = u_lo + warp; u <= u_hi; u += nwarp) {
         double a[33];
         const double* __restrict__ row = A + (size_t)u * APITCH64;
@@ -368,7 +373,7 @@ k_online_select(const double* __restrict__ An64, int T, int B, double thr, int d
             const int k = lane + 32 * i;
             a[i] = k < NBIN ? row[k] : 0.0;
         }
-        const int slot = u % B;
+        const int slot = (u + frame_base) % B;
         for (int f = 0; f < nf; ++f) {
             const int j = j_first + f;
             if (u > j || u < j - (B - 1)) continue;  // warp-uniform
@@ -408,7 +413,7 @@ k_online_select(const double* __restrict__ An64, int T, int B, double thr, int d
             if (x != b && keepf[x]) rank += (sim[x] > v) || (sim[x] == v && x > b);
         atomicAdd(&s_kept[f], 1);
         if (rank < number) {
-            const int j = j_first + f, j0 = j % B;
+            const int j = j_first + f, j0 = (j + frame_base) % B;
             const int frame = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
             idx_out[((size_t)item * T + j) * (size_t)number + rank] = frame;
         }
@@ -417,18 +422,19 @@ k_online_select(const double* __restrict__ An64, int T, int B, double thr, int d
     if (t < nf) cnt_out[(size_t)item * T + j_first + t] = min(s_kept[t], number);
 }
 
-void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, double thr, int d, int number,
-                          int* idx_out, int* cnt_out) {
-    if (T < B) return;
+void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
+                          int d, int number, int* idx_out, int* cnt_out) {
+    const int row_first = std::max(0, B - 1 - frame_base);
+    if (T <= row_first) return;
     const size_t smem = (size_t)ONLINE_FB * APITCH64 * 8 + (size_t)ONLINE_FB * B * 9 + 16;
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
         cudaFuncSetAttribute(k_online_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    const int n_targets = T - (B - 1);
+    const int n_targets = T - row_first;
     dim3 grid((n_targets + ONLINE_FB - 1) / ONLINE_FB, n_items);
-    k_online_select<<<grid, 256, smem, st>>>(An64, T, B, thr, d, number, idx_out, cnt_out);
+    k_online_select<<<grid, 256, smem, st>>>(An64, T, B, frame_base, thr, d, number, idx_out, cnt_out);
 }
 
 // ------------------------------------------------------------------------------------------

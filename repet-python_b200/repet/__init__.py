@@ -140,6 +140,15 @@ def simonline(audio_signal, sampling_frequency):
     return _host.simonline_f64(audio_signal, sampling_frequency, _tunables())
 
 
+class SimOnline(_host.SimOnlineStream):
+    """Streaming front end of the online REPET-SIM: `SimOnline(sampling_frequency, number_channels)`, then
+    `process(block)` per block of samples and `flush()` at the end; the concatenated outputs equal
+    `repet.simonline` on the whole signal.  The module tunables are read at construction."""
+
+    def __init__(self, sampling_frequency, number_channels):
+        super().__init__(sampling_frequency, number_channels, _tunables())
+
+
 def wavread(audio_file):
     """
     Read a WAVE file (using SciPy) (repet.py:914-931).

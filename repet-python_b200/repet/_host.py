@@ -40,7 +40,7 @@ class RepetParams(ctypes.Structure):
         ("similarity_distance", ctypes.c_int32),
         ("similarity_number", ctypes.c_int32),
         ("buffer_frames", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("online_frame_base", ctypes.c_int32),
         ("similarity_threshold", ctypes.c_double),
         ("cola_gain", ctypes.c_double),
     ]
@@ -705,3 +705,88 @@ def original_batch_pcm16(pcm, sampling_frequency, tunables, handle=None):
         )
     )
     return background, periods
+
+
+class SimOnlineStream:
+    """Block-wise online REPET-SIM (repet.py:712-911) with the results of one whole-signal call.
+
+    `process(block)` takes the next samples (n, channels) and returns the background samples that have
+    become final (every frame covering them is complete: a latency of one hop, 1024 samples at 44.1 kHz);
+    `flush()` returns the rest, zero-padding the last frame as the reference does.  Each call re-analyses
+    the last buffer_length seconds on the device (the path runs at >70 000x realtime, so this costs a
+    fraction of a millisecond per second of audio) with the ring-slot order of the whole stream
+    (`online_frame_base`, quirk Q6).  Like the reference, nothing is synthesised before frame
+    buffer_frames-1: the first ~10 s of output are zero.
+    """
+
+    def __init__(self, sampling_frequency, number_channels, tunables, handle=None):
+        self.handle = handle or get_handle()
+        self.fs = sampling_frequency
+        self.channels = int(number_channels)
+        self.tunables = dict(tunables)
+        self.params, _ = derive_params(sampling_frequency, self.tunables, "simonline")
+        self.N, self.H, self.B = self.params.window_length, self.params.step_length, self.params.buffer_frames
+        self.buffer = np.zeros((0, self.channels), dtype=np.float64)  # samples from frame `buffer_frame0` on
+        self.buffer_frame0 = 0
+        self.received = 0
+        self.emitted = 0
+
+    def _run_window(self, first_frame, number_samples):
+        """simonline on buffer samples [first_frame*H - buffer_frame0*H, ... + number_samples)."""
+        lo = (first_frame - self.buffer_frame0) * self.H
+        window = np.ascontiguousarray(self.buffer[lo : lo + number_samples])
+        params = RepetParams()
+        ctypes.memmove(ctypes.byref(params), ctypes.byref(self.params), ctypes.sizeof(RepetParams))
+        params.online_frame_base = int(first_frame)
+        self.handle.ensure_window(params.window_length)
+        out = np.empty_like(window)
+        self.handle.check(
+            self.handle.lib.repet_simonline_f64(
+                self.handle.h, _ptr(window), window.shape[0], self.channels, ctypes.byref(params), _ptr(out), None, 0
+            )
+        )
+        return out
+
+    def _advance(self, final_until, total_samples_for_window):
+        """Emit background samples [emitted, final_until)."""
+        if final_until <= self.emitted:
+            return np.zeros((0, self.channels))
+        first_block = self.emitted // self.H
+        first_needed = max(0, first_block - 1)  # block b mixes frames b-1 and b
+        first_frame = max(0, first_needed - (self.B - 1))  # ... and their similarity history
+        first_frame = max(first_frame, self.buffer_frame0)
+        out = self._run_window(first_frame, total_samples_for_window - first_frame * self.H)
+        lo = self.emitted - first_frame * self.H
+        chunk = out[lo : lo + (final_until - self.emitted)]
+        self.emitted = final_until
+        # drop samples no later window will need
+        keep_frame = max(0, self.emitted // self.H - 1 - (self.B - 1))
+        if keep_frame > self.buffer_frame0:
+            self.buffer = self.buffer[(keep_frame - self.buffer_frame0) * self.H :]
+            self.buffer_frame0 = keep_frame
+        return chunk
+
+    def process(self, block):
+        block = np.asarray(block, dtype=np.float64)
+        if block.ndim != 2 or block.shape[1] != self.channels:
+            raise ValueError("block must have shape (samples, %d)" % self.channels)
+        self.buffer = np.concatenate((self.buffer, block), axis=0)
+        self.received += block.shape[0]
+        if self.received < self.N:
+            return np.zeros((0, self.channels))
+        last_complete = (self.received - self.N) // self.H
+        final_until = (last_complete + 1) * self.H
+        if last_complete < self.B - 1:
+            # nothing is synthesised yet (quirk Q5): the final samples are zeros
+            chunk = np.zeros((max(0, final_until - self.emitted), self.channels))
+            self.emitted = max(self.emitted, final_until)
+            return chunk
+        return self._advance(final_until, last_complete * self.H + self.N)
+
+    def flush(self):
+        """End of stream: everything up to the last received sample."""
+        if self.received <= self.emitted:
+            return np.zeros((0, self.channels))
+        if self.received < (self.B - 2) * self.H + self.N:
+            raise ValueError("operands could not be broadcast together (signal shorter than the buffer)")
+        return self._advance(self.received, self.received)

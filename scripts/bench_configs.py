@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tracks", type=int, default=4)
     ap.add_argument("--tune", default="")
+    ap.add_argument("--stream-seconds", type=int, default=120, help="length of the streamed simonline latency test")
     args = ap.parse_args()
     import repet_synth
 
@@ -93,6 +94,25 @@ def main():
         print(json.dumps(line), flush=True)
         del audio, out
         torch.cuda.empty_cache()
+    if any(name.startswith("cfg5") for name in wanted) and args.stream_seconds > 0:
+        # cfg5: latency per 1 s block of the streaming front end (host NumPy float64 in and out)
+        x = repet_synth.make_clip(7100, args.stream_seconds * FS, redraw_seconds=(60, 120)).T.astype(np.float64)
+        handle.set_stream(None)
+        saved = repet._host._handles.get(0)
+        repet._host._handles[0] = handle
+        stream_obj = repet.SimOnline(FS, 2)
+        latencies = []
+        for k in range(0, len(x), FS):
+            t0 = time.perf_counter()
+            stream_obj.process(x[k : k + FS])
+            latencies.append(1e3 * (time.perf_counter() - t0))
+        stream_obj.flush()
+        steady = np.array(latencies[12:])  # after the 10 s warm-up of the algorithm
+        print(json.dumps({"config": "cfg5_simonline_stream", "block_seconds": 1.0, "blocks": len(steady),
+                          "latency_ms_p50": float(np.percentile(steady, 50)), "latency_ms_p99": float(np.percentile(steady, 99)),
+                          "latency_ms_max": float(steady.max()), "x_realtime_per_stream": 1e3 / float(np.mean(steady))}), flush=True)
+        if saved is not None:
+            repet._host._handles[0] = saved
 
 
 if __name__ == "__main__":

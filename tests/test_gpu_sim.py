@@ -132,3 +132,19 @@ def test_sim_batch_matches_single_calls(repet):
         lists = repet._host.unpack_lists(ints[i], T, 100)
         _assert_lists(lists, np.array([len(v) for v in det["indices"]]), np.concatenate(det["indices"]), "clip %d" % i)
         _assert_signal(background[i].T.astype(np.float64), y_ref, "clip %d" % i)
+
+
+def test_streaming_simonline_equals_whole_signal_call(repet):
+    """1 s blocks through repet.SimOnline reproduce repet.simonline on the whole signal: the windows use
+    the ring-slot order of the whole stream (quirk Q6), so the lists -- and the samples -- are the same."""
+    x = make_golden.case_input(make_golden.DRIVER_CASES["synth_12s"])
+    x = np.concatenate([x, x[: 5 * FS + 77]])  # 17 s: several blocks after the 10 s warm-up
+    whole = repet.simonline(x, FS)
+    stream = repet.SimOnline(FS, x.shape[1])
+    pieces = [stream.process(x[k : k + FS]) for k in range(0, len(x), FS)]
+    pieces.append(stream.flush())
+    streamed = np.concatenate(pieces)
+    assert streamed.shape == whole.shape
+    assert np.all(streamed[: 430 * 1024] == 0)
+    _assert_signal(streamed, whole, "streamed vs whole")
+    assert float(np.max(np.abs(streamed - whole))) <= 1e-6 * float(np.max(np.abs(whole)))
