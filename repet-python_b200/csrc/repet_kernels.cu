@@ -913,39 +913,48 @@ void launch_adaptive_model(cudaStream_t st, const float2* X, int n_items, int T,
 // first `overlap` samples, and simply adds beyond.
 // ------------------------------------------------------------------------------------------
 __global__ void k_xfade(const float* __restrict__ seg_main, const float* __restrict__ seg_last, int n_seg, int seg_len,
-                        int last_len, int step, int nch, long long S, float* __restrict__ out) {
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= S) return;
+                        int last_len, int step, int nch, int S, float* __restrict__ out) {
+    // 32-bit index arithmetic (a clip has fewer than 2^31 samples); 4 consecutive samples per thread
+    const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (u0 >= S) return;
     const int clip = blockIdx.y / nch, c = blockIdx.y - clip * nch;
     const int ov = seg_len - step;
-    int sg_lo = u < seg_len ? 0 : (int)((u - seg_len) / step) + 1;
-    sg_lo = min(sg_lo, n_seg - 1);
-    const int sg_hi = (int)min((long long)(n_seg - 1), u / step);
     const float inv = 1.0f / (float)(2 * ov);
-    float val = 0.f;
-    for (int sg = sg_lo; sg <= sg_hi; ++sg) {
-        const long long k = (long long)sg * step;
-        const long long i = u - k;
-        float x;
-        if (sg < n_seg - 1)
-            x = seg_main[(((size_t)clip * (n_seg - 1) + sg) * nch + c) * (size_t)seg_len + i];
-        else
-            x = seg_last[((size_t)clip * nch + c) * (size_t)last_len + i];
-        if (sg > 0 && i < ov) {
-            const float up = (float)(2 * i + 1) * inv;               // triang(2 ov)[i]
-            const float down = (float)(2 * (ov - 1 - i) + 1) * inv;  // triang(2 ov)[ov + i]
-            val = val * down + x * up;
-        } else {
-            val += x;
+    const float* __restrict__ main_base = seg_main + ((size_t)clip * (n_seg - 1) * nch + c) * (size_t)seg_len;
+    const float* __restrict__ last_base = seg_last + ((size_t)clip * nch + c) * (size_t)last_len;
+    float* __restrict__ dst = out + ((size_t)clip * nch + c) * (size_t)S;
+    // the covering segments of the 4 samples differ at most at segment boundaries: compute per sample,
+    // but share the divisions
+    const int q_hi = u0 / step;
+    const int q_lo = u0 < seg_len ? -1 : (u0 - seg_len) / step;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int u = u0 + e;
+        if (u >= S) break;
+        int sg_hi = q_hi + ((u - q_hi * step) >= step ? 1 : 0);
+        int sg_lo = u < seg_len ? 0 : q_lo + 1 + ((u - seg_len - q_lo * step) >= step ? 1 : 0);
+        sg_hi = min(sg_hi, n_seg - 1);
+        sg_lo = min(sg_lo, n_seg - 1);
+        float val = 0.f;
+        for (int sg = sg_lo; sg <= sg_hi; ++sg) {
+            const int i = u - sg * step;
+            const float x = sg < n_seg - 1 ? main_base[(size_t)sg * nch * seg_len + i] : last_base[i];
+            if (sg > 0 && i < ov) {
+                const float up = (float)(2 * i + 1) * inv;               // triang(2 ov)[i]
+                const float down = (float)(2 * (ov - 1 - i) + 1) * inv;  // triang(2 ov)[ov + i]
+                val = val * down + x * up;
+            } else {
+                val += x;
+            }
         }
+        dst[u] = val;
     }
-    out[((size_t)clip * nch + c) * (size_t)S + u] = val;
 }
 
 void launch_xfade(cudaStream_t st, const float* seg_main, const float* seg_last, int n_clips, int n_seg, int seg_len,
                   int last_len, int step, int nch, long long S, float* out) {
-    dim3 grid((unsigned)((S + 255) / 256), n_clips * nch);
-    k_xfade<<<grid, 256, 0, st>>>(seg_main, seg_last, n_seg, seg_len, last_len, step, nch, S, out);
+    dim3 grid((unsigned)((S + 1023) / 1024), n_clips * nch);
+    k_xfade<<<grid, 256, 0, st>>>(seg_main, seg_last, n_seg, seg_len, last_len, step, nch, (int)S, out);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -296,3 +296,21 @@ def test_original_batch_pcm16_matches_float_path(repet, wav_pcm):
     ref_background, ref_periods = repet.original_batch(audio, FS)
     assert np.array_equal(periods, ref_periods)
     assert np.array_equal(background, ref_background)  # int16 / 2^15 is exact in fp32
+
+
+def test_original_periods_bit_exact_over_many_clips(repet):
+    """24 of the benchmark's 30 s clips: every period equals the float64 oracle's.  The beat spectrum's
+    relative top-1/top-2 gap is printed: the float64 period search has to resolve the smallest one."""
+    audio = _batch(24, 30.0, first=0)
+    _, periods = repet.original_batch(audio, FS)
+    pr2 = oracle.period_range_frames([1, 10], FS, 1024)
+    gaps = []
+    for i in range(audio.shape[0]):
+        x = audio[i].T.astype(np.float64)
+        _, det = oracle.original(x, FS, return_details=True)
+        assert int(periods[i]) == det["period"], "clip %d: gpu %d, oracle %d" % (i, periods[i], det["period"])
+        b = det["beat_spectrum"]
+        hi = min(int(pr2[1]), len(b) // 3)
+        window = np.sort(b[int(pr2[0]) : hi])
+        gaps.append(float((window[-1] - window[-2]) / window[-1]))
+    print("relative top-2 gaps of the beat spectrum: min %.3e, median %.3e" % (min(gaps), float(np.median(gaps))))
