@@ -175,6 +175,7 @@ int repet_set_tuning(const char* name, int value) {
     else if (key == "frames_per_cta") g_tuning.frames_per_cta = value;
     else if (key == "beat_parts") g_tuning.beat_parts = value;
     else if (key == "simgemm_tc") g_tuning.simgemm_tc = value;
+    else if (key == "cert_rel_ppm") g_tuning.cert_rel_ppm = value;
     else return REPET_E_INVALID_ARG;
     return REPET_OK;
 }
@@ -295,7 +296,7 @@ static int beat_common(repet_handle* h, const float* spectrogram, int n_frames, 
                          n_frames, cudaMemcpyHostToDevice, st));
     launch_beat(st, P, 1, n_frames, 0, n_frames, 0, 1, tables(h), psd, n_parts, f_per_part);
     launch_periods(st, psd, nullptr, 1, n_parts, n_frames, (double)n_rows, lag_lo, lag_hi, 0, beat ? n_frames : 0,
-                   beat ? b : nullptr, BEAT_L, period ? per : nullptr, nullptr);
+                   beat ? b : nullptr, BEAT_L, period ? per : nullptr, nullptr, nullptr);
     h->launches += 2;
     if (beat) CU(cudaMemcpyAsync(beat, b, (size_t)n_frames * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (period) CU(cudaMemcpyAsync(period, per, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -417,7 +418,7 @@ int repet_beatspectrogram(repet_handle* h, const float* spectrogram, int n_frame
     const int left = segment_length / 2;  // ceil((L-1)/2), repet.py:1182
     launch_beat(st, P, 1, n_frames, -left, segment_length, segment_step, n_seg, tables(h), psd, n_parts, f_per_part);
     launch_periods(st, psd, nullptr, n_seg, n_parts, segment_length, (double)n_rows, 0, 0, 0, segment_length, b, segment_length,
-                   nullptr, nullptr);
+                   nullptr, nullptr, nullptr);
     h->launches += 2;
     CU(cudaMemcpyAsync(beat, b, (size_t)n_seg * segment_length * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -608,7 +609,7 @@ int repet_acorr(repet_handle* h, const float* data, int n_rows, int n_columns, d
             CU(cudaMemcpy2DAsync(P + (size_t)c * n_rows * PPITCH, PPITCH * sizeof(float), data + c0 + c,
                                  n_columns * sizeof(float), sizeof(float), n_rows, cudaMemcpyHostToDevice, st));
         launch_beat(st, P, g, n_rows, 0, n_rows, 0, 1, tables(h), psd, 1, 8);
-        launch_periods(st, psd, nullptr, g, 1, n_rows, 1.0, 0, 0, 0, n_rows, b, n_rows, nullptr, nullptr);
+        launch_periods(st, psd, nullptr, g, 1, n_rows, 1.0, 0, 0, 0, n_rows, b, n_rows, nullptr, nullptr, nullptr);
         h->launches += 2;
         CU(cudaMemcpyAsync(host.data(), b, (size_t)g * n_rows * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

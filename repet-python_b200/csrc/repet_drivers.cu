@@ -67,7 +67,7 @@ int period_shape(repet_handle* h, const repet_params* p, int nch, int64_t n_samp
     b += align_up((size_t)T * PPITCH * sizeof(float));
     b += (s->n_blocks > 1 ? 2 : 1) * align_up((size_t)s->n_blocks * s->n_parts * BEAT_L * sizeof(float));
     b += align_up((size_t)nch * s->pmax * PPITCH * sizeof(float));
-    b += 512;
+    b += 2048;  // period certification records
     s->bytes_per_item = b;
     return REPET_OK;
 }
@@ -97,6 +97,8 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
         float* psd = bump.take<float>((size_t)g_items * total_parts * BEAT_L);
         float* psd_im = blocked ? bump.take<float>((size_t)g_items * total_parts * BEAT_L) : nullptr;
         float* model = bump.take<float>((size_t)g_items * nch * s.pmax * PPITCH);
+        int* cert = bump.take<int>((size_t)g_items * (CERT_MAX + 1));
+        double* cert_val = bump.take<double>((size_t)g_items * CERT_MAX * 16);  // x CERT_TSPLIT partial sums
         gin.n_items = gout.n_items = g_items;
         gin.item0 = gout.item0 = first;
         const int K = pick_frames_per_cta(h, (long long)g_items * s.T);
@@ -115,7 +117,8 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
         {
             Timed timed(h, REPET_K_PERIODS);
             launch_periods(st, psd, psd_im, g_items, total_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr,
-                           0, periods_dev + first, nullptr);
+                           0, periods_dev + first, nullptr, cert);
+            launch_period_certify(st, P, g_items, s.T, cert, cert_val, periods_dev + first);
         }
         {
             Timed timed(h, REPET_K_MODEL);
@@ -448,7 +451,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         {
             Timed timed(h, REPET_K_PERIODS);
             launch_periods(st, psd, nullptr, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
-                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr);
+                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr, nullptr);
         }
         {
             Timed timed(h, REPET_K_MODEL);

@@ -274,7 +274,7 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
 __global__ void __launch_bounds__(256)
 k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part_im, int n_parts, int t_len,
           double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* __restrict__ beat_out,
-          int beat_pitch, int* __restrict__ period, double* __restrict__ stats) {
+          int beat_pitch, int* __restrict__ period, double* __restrict__ stats, int* __restrict__ cert, double cert_rel) {
     extern __shared__ __align__(16) unsigned char s_raw_periods[];
     double* s_cos = reinterpret_cast<double*>(s_raw_periods);  // [BEAT_L]      cos(2 pi k / L)
     double* s_b = s_cos + BEAT_L;                              // [BEAT_L]      partial sums, then b[l]
@@ -342,6 +342,14 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
             }
         }
         period[bi] = arg + 1;
+        if (cert) {
+            // lags whose value is within CERT_REL of the best: k_period_certify re-evaluates them exactly
+            int n = 0;
+            const double floor_v = best - fabs(best) * cert_rel;
+            for (int l = lag_lo; l < lag_hi && n < CERT_MAX; ++l)
+                if (s_b[l] >= floor_v) cert[bi * (CERT_MAX + 1) + 1 + n++] = l;
+            cert[bi * (CERT_MAX + 1)] = n >= 2 ? n : 0;
+        }
         if (stats) {
             stats[4 * bi + 0] = best;
             stats[4 * bi + 1] = second;
@@ -353,7 +361,7 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
 
 void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_part_im, int n_beat_items, int n_parts,
                     int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
-                    int beat_pitch, int* period, double* stats) {
+                    int beat_pitch, int* period, double* stats, int* cert) {
     const size_t smem = (size_t)(2 * BEAT_L + 2 * (BEAT_L / 2 + 1)) * sizeof(double);
     static bool configured = false;
     if (!configured) {
@@ -361,7 +369,80 @@ void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_par
         configured = true;
     }
     k_periods<<<n_beat_items, 256, smem, st>>>(psd_part, psd_part_im, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo,
-                                              out_hi, beat_out, beat_pitch, period, stats);
+                                              out_hi, beat_out, beat_pitch, period, stats, cert,
+                                              g_tuning.cert_rel_ppm > 0 ? 1e-6 * g_tuning.cert_rel_ppm : CERT_REL);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_period_certify / k_period_finalize  --  near-tied period candidates decided in float64
+// When several lags sit within CERT_REL of the maximum of the beat spectrum, the fp32 time-axis
+// transforms of k_beat could flip their order.  Each candidate lag is re-evaluated exactly,
+// b[l] = (1/(T-l)) sum_f sum_t P[f,t] P[f,t+l] accumulated in float64 straight from P (the 1/F factor
+// is common), and the first maximum wins, as np.argmax does.  CTAs of unflagged clips exit at once.
+// ------------------------------------------------------------------------------------------
+constexpr int CERT_TSPLIT = 16;  // time chunks per candidate (partial sums are added in a fixed order)
+
+__global__ void __launch_bounds__(256)
+k_period_certify(const float* __restrict__ P, int T, const int* __restrict__ cert, double* __restrict__ cert_part) {
+    const int item = blockIdx.y, slot = blockIdx.x, chunk = blockIdx.z;
+    const int n = cert[item * (CERT_MAX + 1)];
+    if (slot >= n) return;
+    const int lag = cert[item * (CERT_MAX + 1) + 1 + slot];
+    const float* __restrict__ Pi = P + (size_t)item * T * PPITCH;
+    const int rows = T - lag;
+    const int per = (rows + CERT_TSPLIT - 1) / CERT_TSPLIT;
+    const int t_begin = chunk * per, t_end = min(rows, t_begin + per);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int t = t_begin + warp; t < t_end; t += 8) {
+        const float* __restrict__ a = Pi + (size_t)t * PPITCH;
+        const float* __restrict__ b = Pi + (size_t)(t + lag) * PPITCH;
+        float av[33], bv[33];
+#pragma unroll
+        for (int i = 0; i < 33; ++i) {
+            const int f = lane + 32 * i;
+            av[i] = f < NBIN ? __ldg(a + f) : 0.f;
+            bv[i] = f < NBIN ? __ldg(b + f) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 33; ++i) acc = fma((double)av[i], (double)bv[i], acc);
+    }
+    __shared__ double s_red[256];
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cert_part[((size_t)item * CERT_MAX + slot) * CERT_TSPLIT + chunk] = s_red[0];
+}
+
+__global__ void k_period_finalize(const int* __restrict__ cert, const double* __restrict__ cert_part, int n_items, int T,
+                                  int* __restrict__ period) {
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    const int n = cert[item * (CERT_MAX + 1)];
+    if (n < 2) return;
+    int arg = -1;
+    double best = 0.0;
+    for (int s = 0; s < n; ++s) {
+        const int lag = cert[item * (CERT_MAX + 1) + 1 + s];
+        double v = 0.0;
+        for (int c = 0; c < CERT_TSPLIT; ++c) v += cert_part[((size_t)item * CERT_MAX + s) * CERT_TSPLIT + c];
+        v /= (double)(T - lag);
+        if (arg < 0 || v > best) {  // candidates are in ascending lag order: strict > keeps the first maximum
+            best = v;
+            arg = lag;
+        }
+    }
+    period[item] = arg + 1;
+}
+
+void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, const int* cert, double* cert_val,
+                           int* period) {
+    dim3 grid(CERT_MAX, n_items, CERT_TSPLIT);
+    k_period_certify<<<grid, 256, 0, st>>>(P, T, cert, cert_val);
+    k_period_finalize<<<(n_items + 127) / 128, 128, 0, st>>>(cert, cert_val, n_items, T, period);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -48,6 +48,7 @@ struct Tuning {
     int mask_minb = 5;       // same for the mask+ISTFT kernel
     int frames_per_cta = 0;  // 0 = pick from the batch size
     int beat_parts = 0;      // 0 = pick from the batch size
+    int cert_rel_ppm = 0;    // period certification window in ppm of the best value (0 = CERT_REL = 100 ppm)
     int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
 };
 extern Tuning g_tuning;
@@ -64,7 +65,12 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
 // k_periods: partial PSDs -> beat spectrum b[l] (optional) and argmax period per beat item (fp64)
 void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_part_im, int n_beat_items, int n_parts,
                     int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
-                    int beat_pitch, int* period, double* stats);
+                    int beat_pitch, int* period, double* stats, int* cert);
+// near-tied period candidates re-decided in float64 (cert: [item][1 + CERT_MAX] ints written by k_periods)
+constexpr int CERT_MAX = 8;
+constexpr double CERT_REL = 1e-4;
+void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, const int* cert, double* cert_val,
+                           int* period);
 // k_beat_blocked: clips longer than one transform, complex cross-spectrum partials
 // g_re / g_im [item][block][fpart][2048]
 void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, int Bk, int max_lag, FftTables tb,

@@ -314,3 +314,19 @@ def test_original_periods_bit_exact_over_many_clips(repet):
         window = np.sort(b[int(pr2[0]) : hi])
         gaps.append(float((window[-1] - window[-2]) / window[-1]))
     print("relative top-2 gaps of the beat spectrum: min %.3e, median %.3e" % (min(gaps), float(np.median(gaps))))
+
+
+def test_period_certification_path(repet):
+    """Force the float64 re-evaluation of near-tied lags (window widened from 100 ppm to 20 %): the
+    certified periods must equal the oracle's, i.e. the exact path agrees with the fast one."""
+    audio = _batch(6, 20.0, first=300)
+    _, fast = repet.original_batch(audio, FS)
+    repet._host.set_tuning(cert_rel_ppm=200000)
+    try:
+        background, certified = repet.original_batch(audio, FS)
+    finally:
+        repet._host.set_tuning(cert_rel_ppm=0)
+    assert np.array_equal(fast, certified)
+    for i in range(audio.shape[0]):
+        _, det = oracle.original(audio[i].T.astype(np.float64), FS, return_details=True)
+        assert int(certified[i]) == det["period"], i
