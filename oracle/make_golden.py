@@ -48,12 +48,32 @@ DRIVER_CASES = {
 }
 
 
+# other sampling rates: window lengths 512 (8 kHz), 1024 (16, 22.05 kHz) and 2048 with another
+# hop / period mapping (48 kHz); repet.py:130 (quirk Q16).  Written to drivers_rates.npz.
+RATE_CASES = {
+    "synth16k_12s": dict(kind="synth", fs=16000, index=21, samples=12 * 16000 + 123, channels=2,
+                         functions=["original", "extended", "adaptive", "sim", "simonline"]),
+    "synth8k_14s": dict(kind="synth", fs=8000, index=23, samples=14 * 8000 + 57, channels=2,
+                        functions=["original", "extended", "adaptive", "sim", "simonline"]),
+    "synth22k_mono_9s": dict(kind="synth", fs=22050, index=25, samples=9 * 22050, channels=1,
+                             functions=["original", "adaptive", "sim"]),
+    "synth48k_6s": dict(kind="synth", fs=48000, index=27, samples=6 * 48000 + 5, channels=2,
+                        functions=["original", "sim"]),
+}
+
+
+def case_fs(spec):
+    return spec.get("fs", FS)
+
+
 def case_input(spec, wav=None):
     """(S, C) float64 input of a driver case.  Shared with tests/ (imported from there)."""
     if spec["kind"] == "wav":
         pcm = wav[spec["start"] : spec["stop"]]
         return pcm / pow(2, pcm.itemsize * 8 - 1)  # repet.py:929
-    clip = repet_synth.make_clip(spec["index"], spec["samples"], spec["channels"], FS)
+    fs = case_fs(spec)
+    step_length = oracle.stft_parameters(fs)[2]
+    clip = repet_synth.make_clip(spec["index"], spec["samples"], spec["channels"], fs, step_length)
     return clip.T.astype(np.float64)
 
 
@@ -83,6 +103,51 @@ def _close(a, b, what):
     scale = max(np.max(np.abs(a)) if a.size else 0.0, 1e-300)
     err = np.max(np.abs(a - b)) / scale if a.size else 0.0
     assert err <= 1e-12, (what, err)
+
+
+def pin_drivers(ref, cases, wav=None):
+    """Run the reference and the oracle on every case, assert they agree, return the reference's outputs."""
+    drivers = {}
+    for case, spec in cases.items():
+        x = case_input(spec, wav)
+        FS = case_fs(spec)
+        for fn in spec["functions"]:
+            key = "%s/%s" % (case, fn)
+            y_ref = getattr(ref, fn)(x, FS)
+            y_orc, det = getattr(oracle, fn)(x, FS, return_details=True)
+            _close(y_ref, y_orc, key)
+            drivers[key + "/rms"] = np.sqrt(np.mean(np.square(y_ref)))
+            drivers[key + "/max"] = np.max(np.abs(y_ref))
+            drivers[key + "/dec"] = y_ref[::DECIMATE].copy()
+            # integer outputs: recompute from the REFERENCE's own helpers
+            N, w, H = oracle.stft_parameters(FS)
+            C = x.shape[1]
+            if fn in ("original", "adaptive", "sim"):
+                spec_ref = np.stack([np.abs(ref._stft(x[:, c], w, H)[0 : N // 2 + 1]) for c in range(C)], axis=2)
+                pr2 = np.round(np.array(ref.period_range) * FS / H).astype(int)
+            if fn == "original":
+                p = ref._periods(ref._beatspectrum(np.power(np.mean(spec_ref, axis=2), 2)), pr2)
+                assert int(p) == det["period"], key
+                drivers[key + "/period"] = np.int64(p)
+            elif fn == "adaptive":
+                B = ref._beatspectrogram(np.power(np.mean(spec_ref, axis=2), 2), int(round(10 * FS / H)), int(round(5 * FS / H)))
+                p = ref._periods(B, pr2)
+                assert np.array_equal(p, det["periods"]), key
+                drivers[key + "/periods"] = p.astype(np.int64)
+            elif fn == "sim":
+                Sm = ref._selfsimilaritymatrix(np.mean(spec_ref, axis=2))
+                lists = ref._indices(Sm, 0, int(round(FS / H)), 100)
+                assert all(np.array_equal(a, b) for a, b in zip(lists, det["indices"])), key
+                drivers[key + "/index_counts"] = np.array([len(v) for v in lists], dtype=np.int64)
+                drivers[key + "/index_flat"] = np.concatenate(lists).astype(np.int64)
+            elif fn == "extended":
+                drivers[key + "/periods"] = np.array(det["periods"], dtype=np.int64)
+            elif fn == "simonline":
+                drivers[key + "/index_counts"] = np.array([len(v) for v in det["indices"]], dtype=np.int64)
+                drivers[key + "/index_flat"] = np.concatenate(det["indices"]).astype(np.int64)
+                drivers[key + "/first_frame"] = np.int64(det["first_frame"])
+            print("%-28s rms %.17g  pinned" % (key, drivers[key + "/rms"]))
+    return drivers
 
 
 def main():
@@ -143,48 +208,15 @@ def main():
     print("helpers: %d vectors pinned" % len(pairs))
 
     # ---- driver-level cases -----------------------------------------------------------
-    drivers = {}
-    for case, spec in DRIVER_CASES.items():
-        x = case_input(spec, wav)
-        for fn in spec["functions"]:
-            key = "%s/%s" % (case, fn)
-            y_ref = getattr(ref, fn)(x, FS)
-            y_orc, det = getattr(oracle, fn)(x, FS, return_details=True)
-            _close(y_ref, y_orc, key)
-            drivers[key + "/rms"] = np.sqrt(np.mean(np.square(y_ref)))
-            drivers[key + "/max"] = np.max(np.abs(y_ref))
-            drivers[key + "/dec"] = y_ref[::DECIMATE].copy()
-            # integer outputs: recompute from the REFERENCE's own helpers
-            N, w, H = oracle.stft_parameters(FS)
-            C = x.shape[1]
-            if fn in ("original", "adaptive", "sim"):
-                spec_ref = np.stack([np.abs(ref._stft(x[:, c], w, H)[0 : N // 2 + 1]) for c in range(C)], axis=2)
-                pr2 = np.round(np.array(ref.period_range) * FS / H).astype(int)
-            if fn == "original":
-                p = ref._periods(ref._beatspectrum(np.power(np.mean(spec_ref, axis=2), 2)), pr2)
-                assert int(p) == det["period"], key
-                drivers[key + "/period"] = np.int64(p)
-            elif fn == "adaptive":
-                B = ref._beatspectrogram(np.power(np.mean(spec_ref, axis=2), 2), int(round(10 * FS / H)), int(round(5 * FS / H)))
-                p = ref._periods(B, pr2)
-                assert np.array_equal(p, det["periods"]), key
-                drivers[key + "/periods"] = p.astype(np.int64)
-            elif fn == "sim":
-                Sm = ref._selfsimilaritymatrix(np.mean(spec_ref, axis=2))
-                lists = ref._indices(Sm, 0, int(round(FS / H)), 100)
-                assert all(np.array_equal(a, b) for a, b in zip(lists, det["indices"])), key
-                drivers[key + "/index_counts"] = np.array([len(v) for v in lists], dtype=np.int64)
-                drivers[key + "/index_flat"] = np.concatenate(lists).astype(np.int64)
-            elif fn == "extended":
-                drivers[key + "/periods"] = np.array(det["periods"], dtype=np.int64)
-            elif fn == "simonline":
-                drivers[key + "/index_counts"] = np.array([len(v) for v in det["indices"]], dtype=np.int64)
-                drivers[key + "/index_flat"] = np.concatenate(det["indices"]).astype(np.int64)
-                drivers[key + "/first_frame"] = np.int64(det["first_frame"])
-            print("%-28s rms %.17g  pinned" % (key, drivers[key + "/rms"]))
+    if "--rates-only" not in sys.argv:
+        drivers = pin_drivers(ref, DRIVER_CASES, wav)
+        for k, v in provenance.items():
+            drivers["provenance/" + k] = np.array(v)
+        np.savez_compressed(os.path.join(GOLDEN, "drivers.npz"), **drivers)
+    rates = pin_drivers(ref, RATE_CASES)
     for k, v in provenance.items():
-        drivers["provenance/" + k] = np.array(v)
-    np.savez_compressed(os.path.join(GOLDEN, "drivers.npz"), **drivers)
+        rates["provenance/" + k] = np.array(v)
+    np.savez_compressed(os.path.join(GOLDEN, "drivers_rates.npz"), **rates)
     sizes = {f: os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN)}
     print("written:", sizes)
 

@@ -104,7 +104,7 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
         const int K = pick_frames_per_cta(h, (long long)g_items * s.T);
         {
             Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, gin, nch, h->window, tables(h), X, P, P_POWER, K);
+            launch_stft(st, audio, gin, nch, window_of(h), tables(h), X, P, P_POWER, K);
         }
         {
             Timed timed(h, REPET_K_BEAT);
@@ -318,7 +318,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         const int K = pick_frames_per_cta(h, (long long)g * T);
         {
             Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, geom, nch, h->window, tables(h), X, V, P_MAGNITUDE, K);
+            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, V, P_MAGNITUDE, K);
         }
         {
             Timed timed(h, REPET_K_NORMALIZE);
@@ -440,7 +440,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         const int K = pick_frames_per_cta(h, (long long)g * T);
         {
             Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, geom, nch, h->window, tables(h), X, P, P_POWER, K);
+            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, P, P_POWER, K);
         }
         {
             // segment i spans frames [i - left_pad, i - left_pad + L) (zero outside), repet.py:1177-1198
@@ -622,90 +622,20 @@ int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nc
 
 }  // namespace
 
-extern "C" {
+namespace repet {
 
-// ---- repet.original (repet.py:67-202) ------------------------------------------------------
-int repet_original_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
-    return batch_dev(h, KIND_ORIGINAL, audio, n_clips, n_channels, n_samples, p, background, periods_dev, periods_host, nullptr);
+int drv_batch_dev(repet_handle* h, int kind, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                  const repet_params* p, float* background, int32_t* ints_dev, int32_t* ints_host) {
+    return batch_dev(h, kind, audio, n_clips, n_channels, n_samples, p, background, ints_dev, ints_host, nullptr);
 }
-int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                         const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_ORIGINAL, audio, false, n_clips, n_channels, n_samples, p, background, periods_host);
+int drv_batch_host(repet_handle* h, int kind, const void* audio, int pcm16, int n_clips, int n_channels,
+                   int64_t n_samples, const repet_params* p, float* background, int32_t* ints) {
+    return batch_host(h, kind, audio, pcm16 != 0, n_clips, n_channels, n_samples, p, background, ints);
 }
-int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
-                       double* background, int32_t* period_host) {
-    return single_f64(h, KIND_ORIGINAL, audio, n_samples, n_channels, p, background, period_host, 1);
-}
-
-int repet_original_batch_pcm16(repet_handle* h, const int16_t* audio, int n_clips, int n_channels, int64_t n_samples,
-                               const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_ORIGINAL, audio, true, n_clips, n_channels, n_samples, p, background, periods_host);
+int drv_single_f64(repet_handle* h, int kind, const double* audio, int64_t n_samples, int n_channels,
+                   const repet_params* p, double* background, int32_t* ints, int64_t ints_capacity) {
+    return single_f64(h, kind, audio, n_samples, n_channels, p, background, ints,
+                      (int)std::min<int64_t>(ints_capacity, INT32_MAX));
 }
 
-// ---- repet.extended (repet.py:205-419) -----------------------------------------------------
-int repet_extended_segments(const repet_params* p, int64_t n_samples) {
-    if (!p || p->segment_length <= 0 || p->segment_step <= 0) return 0;
-    if (n_samples < (int64_t)p->segment_length + p->segment_step) return 1;
-    return 1 + (int)((n_samples - p->segment_length) / p->segment_step);
-}
-int repet_extended_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
-    return batch_dev(h, KIND_EXTENDED, audio, n_clips, n_channels, n_samples, p, background, periods_dev, periods_host, nullptr);
-}
-int repet_extended_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                         const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_EXTENDED, audio, false, n_clips, n_channels, n_samples, p, background, periods_host);
-}
-int repet_extended_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
-                       double* background, int32_t* periods_host, int periods_capacity) {
-    return single_f64(h, KIND_EXTENDED, audio, n_samples, n_channels, p, background, periods_host, periods_capacity);
-}
-
-// ---- repet.adaptive (repet.py:422-568) -----------------------------------------------------
-int repet_adaptive_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                             const repet_params* p, float* background, int32_t* periods_dev, int32_t* periods_host) {
-    return batch_dev(h, KIND_ADAPTIVE, audio, n_clips, n_channels, n_samples, p, background, periods_dev, periods_host, nullptr);
-}
-int repet_adaptive_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                         const repet_params* p, float* background, int32_t* periods_host) {
-    return batch_host(h, KIND_ADAPTIVE, audio, false, n_clips, n_channels, n_samples, p, background, periods_host);
-}
-int repet_adaptive_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
-                       double* background, int32_t* periods_host, int periods_capacity) {
-    return single_f64(h, KIND_ADAPTIVE, audio, n_samples, n_channels, p, background, periods_host, periods_capacity);
-}
-
-// ---- repet.sim (repet.py:571-709) ----------------------------------------------------------
-int repet_sim_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                        const repet_params* p, float* background, int32_t* lists_dev, int32_t* lists_host) {
-    return batch_dev(h, KIND_SIM, audio, n_clips, n_channels, n_samples, p, background, lists_dev, lists_host, nullptr);
-}
-int repet_sim_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                    const repet_params* p, float* background, int32_t* lists_host) {
-    return batch_host(h, KIND_SIM, audio, false, n_clips, n_channels, n_samples, p, background, lists_host);
-}
-int repet_sim_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
-                  double* background, int32_t* lists_host, int lists_capacity) {
-    return single_f64(h, KIND_SIM, audio, n_samples, n_channels, p, background, lists_host, lists_capacity);
-}
-
-// ---- repet.simonline (repet.py:712-911) ----------------------------------------------------
-int repet_simonline_frames(const repet_params* p, int64_t n_samples) {
-    if (!p || n_samples < p->window_length) return 0;
-    return (int)((n_samples - p->window_length + p->step_length - 1) / p->step_length) + 1;
-}
-int repet_simonline_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                              const repet_params* p, float* background, int32_t* lists_dev, int32_t* lists_host) {
-    return batch_dev(h, KIND_SIMONLINE, audio, n_clips, n_channels, n_samples, p, background, lists_dev, lists_host, nullptr);
-}
-int repet_simonline_batch(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
-                          const repet_params* p, float* background, int32_t* lists_host) {
-    return batch_host(h, KIND_SIMONLINE, audio, false, n_clips, n_channels, n_samples, p, background, lists_host);
-}
-int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
-                        double* background, int32_t* lists_host, int lists_capacity) {
-    return single_f64(h, KIND_SIMONLINE, audio, n_samples, n_channels, p, background, lists_host, lists_capacity);
-}
-
-}  // extern "C"
+}  // namespace repet

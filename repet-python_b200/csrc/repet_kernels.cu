@@ -9,10 +9,13 @@
 // Frames are the slow axis, bins the fast one: every gather along time (period-strided
 // medians, similar-frame medians) is a coalesced row read.
 #include "repet_kernels.cuh"
-#include "fft2048.cuh"
+#include "fft_core.cuh"
 #include "median_networks.cuh"
 
 namespace repet {
+
+using FF = Fft<WIN_N>;  // frame transforms (STFT / ISTFT)
+using TF = Fft<2048>;   // time-axis transforms of the beat spectrum
 
 
 // ------------------------------------------------------------------------------------------
@@ -40,22 +43,22 @@ __device__ __forceinline__ void stft_emit(float2 a, float2 b, int k, float2* __r
 }
 
 template <int NCH, int MINB>
-__global__ void __launch_bounds__(FFT_THREADS, MINB)
+__global__ void __launch_bounds__(FF::THREADS, MINB)
 k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window, FftTables tb,
        float2* __restrict__ X, float* __restrict__ P, int pmode, int K) {
-    __shared__ float2 s_bufA[FFT_BUF];
-    __shared__ float2 s_bufB[FFT_BUF];
-    __shared__ float2 s_tw2[128];
+    __shared__ float2 s_bufA[FF::BUF];
+    __shared__ float2 s_bufB[FF::BUF];
+    __shared__ float2 s_tw2[FF::TW2];
     const int t = threadIdx.x;
     const int item = blockIdx.y;
     const int j0 = blockIdx.x * K;
     const int j1 = min(j0 + K, g.T);
     s_tw2[t] = tb.tw2[t];
-    Twiddle1 tw;
+    FF::Twiddle1 tw;
     tw.load(tb.tw1, t);
     float wv[16];  // half the window: the 1/2 of the channel split is folded in here
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) wv[n1] = 0.5f * __ldg(&window[n1 * 128 + t]);
+    for (int n1 = 0; n1 < 16; ++n1) wv[n1] = 0.5f * __ldg(&window[n1 * FF::THREADS + t]);
     const int gitem = g.item0 + item;
     const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
     const float* __restrict__ a0 = audio + g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
@@ -66,7 +69,7 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
         const long long base = (long long)(j0 - 1 + g.frame_shift) * HOP + t;
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
-            const long long idx = base + n1 * 128;
+            const long long idx = base + n1 * FF::THREADS;
             const bool ok = idx >= 0 && idx < g.S;
             cl[n1] = ok ? __ldg(a0 + idx) : 0.f;
             cr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
@@ -77,21 +80,22 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
         float2 r[16];
         const long long base = (long long)(j + g.frame_shift) * HOP + t;  // second half of frame j
         // pull the next frame's new half (2 x 4 KB) towards L2 while this frame is transformed
-        if (t < 64 && j + 1 < j1) {
-            const long long nxt = base - t + HOP + (t & 31) * 32;
-            if (nxt < g.S) prefetch_l2((t < 32 || NCH == 1 ? a0 : a1) + nxt);
+        constexpr int LINES = HOP / 32;  // 128-byte lines of one channel's half frame
+        if (t < NCH * LINES && j + 1 < j1) {
+            const long long nxt = base - t + HOP + (t % LINES) * 32;
+            if (nxt < g.S) prefetch_l2((t < LINES ? a0 : a1) + nxt);
         }
         float nl[8], nr[8];
         if (base - t + HOP <= g.S) {  // whole half frame inside the signal: no bounds checks
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
-                nl[n1] = __ldg(a0 + base + n1 * 128);
-                nr[n1] = NCH == 2 ? __ldg(a1 + base + n1 * 128) : 0.f;
+                nl[n1] = __ldg(a0 + base + n1 * FF::THREADS);
+                nr[n1] = NCH == 2 ? __ldg(a1 + base + n1 * FF::THREADS) : 0.f;
             }
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
-                const long long idx = base + n1 * 128;
+                const long long idx = base + n1 * FF::THREADS;
                 const bool ok = idx < g.S;
                 nl[n1] = ok ? __ldg(a0 + idx) : 0.f;
                 nr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
@@ -104,12 +108,12 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
             cl[n1] = nl[n1];
             cr[n1] = nr[n1];
         }
-        fft_stage1(r, tw, s_bufA, t);
+        FF::stage1(r, tw, s_bufA, t);
         __syncthreads();
-        fft_stage2(r, s_bufA, s_bufB, s_tw2, t);
+        FF::stage2(r, s_bufA, s_bufB, s_tw2, t);
         __syncthreads();
-        fft_stage3(r, s_bufB, t);
-        // the thread now holds Z[k]/2 and Z[2048-k]/2 for its 8 bins k < 1024: split in registers
+        FF::stage3(r, s_bufB, t);
+        // the thread now holds Z[k]/2 and Z[N-k]/2 for its 8 bins k < N/2: split in registers
         const size_t frame = (size_t)item * g.T + j;
         float2* __restrict__ xrow = X + frame * (size_t)(NCH * XPITCH);
         float* __restrict__ prow = P ? P + frame * (size_t)PPITCH : nullptr;
@@ -119,7 +123,7 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k3 = 0; k3 < 4; ++k3)
-                    stft_emit<NCH>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3], (h == 0 ? t : 256 - t) + 256 * k3, xrow, prow, pmode);
+                    stft_emit<NCH>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3], (h == 0 ? t : FF::CCOLS - t) + FF::CCOLS * k3, xrow, prow, pmode);
         } else {
             // thread 0 owns the self-mirrored columns 0 and 128; bin 0 packs (DC, Nyquist), both real
             const float2 dc = r[0], ny = r[4];
@@ -132,19 +136,18 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
                 prow[XPITCH] = pmode == P_POWER ? mn * mn : mn;
             }
 #pragma unroll
-            for (int k3 = 1; k3 < 4; ++k3) stft_emit<NCH>(r[k3], r[8 - k3], 256 * k3, xrow, prow, pmode);
+            for (int k3 = 1; k3 < 4; ++k3) stft_emit<NCH>(r[k3], r[8 - k3], FF::CCOLS * k3, xrow, prow, pmode);
 #pragma unroll
-            for (int k3 = 0; k3 < 4; ++k3) stft_emit<NCH>(r[8 + k3], r[8 + 7 - k3], 128 + 256 * k3, xrow, prow, pmode);
+            for (int k3 = 0; k3 < 4; ++k3) stft_emit<NCH>(r[8 + k3], r[8 + 7 - k3], FF::THREADS + FF::CCOLS * k3, xrow, prow, pmode);
         }
     }
 }
 
-Tuning g_tuning;
 
 void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,
                  float* P, int pmode, int frames_per_cta) {
     dim3 grid((g.T + frames_per_cta - 1) / frames_per_cta, g.n_items);
-#define REPET_GO(NCH, MINB) k_stft<NCH, MINB><<<grid, FFT_THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta)
+#define REPET_GO(NCH, MINB) k_stft<NCH, MINB><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta)
     if (nch == 2) {
         if (g_tuning.stft_minb >= 6) REPET_GO(2, 6);
         else if (g_tuning.stft_minb == 5) REPET_GO(2, 5);
@@ -176,23 +179,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(FFT_THREADS)
+__global__ void __launch_bounds__(TF::THREADS)
 k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step, int n_seg, FftTables tb,
        float* __restrict__ psd_part, int n_parts, int f_per_part, int TP) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float2* s_bufA = reinterpret_cast<float2*>(s_raw);
-    float2* s_bufB = s_bufA + FFT_BUF;
-    float2* s_tw2 = s_bufB + FFT_BUF;
-    float4* s_tile = reinterpret_cast<float4*>(s_tw2 + 128);  // 2 x [TP] frames x 4 rows (16 B per frame)
+    float2* s_bufB = s_bufA + TF::BUF;
+    float2* s_tw2 = s_bufB + TF::BUF;
+    float4* s_tile = reinterpret_cast<float4*>(s_tw2 + TF::TW2);  // 2 x [TP] frames x 4 rows (16 B per frame)
     const int t = threadIdx.x;
     const int bi = blockIdx.y;
     const int item = bi / n_seg, sg = bi - item * n_seg;
     const int ts = t_first + sg * seg_step;
     const int f_begin = blockIdx.x * f_per_part;
     const int f_end = min(NBIN, f_begin + f_per_part);
-    s_tw2[t] = tb.tw2[t];
-    Twiddle1 tw;
-    tw.load(tb.tw1, t);
+    s_tw2[t] = tb.tw2_t[t];
+    TF::Twiddle1 tw;
+    tw.load(tb.tw1_t, t);
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -201,7 +204,7 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
     // two transforms of tile i run.  Rows >= 1025 are the zero padding of P.
     auto fetch = [&](int f0, int buf) {
         float4* dst = s_tile + buf * TP;
-        for (int row = t; row < t_len; row += FFT_THREADS) {
+        for (int row = t; row < t_len; row += TF::THREADS) {
             const int frame = ts + row;
             const bool ok = frame >= 0 && frame < T;
             cp_async16(dst + row, Pitem + (size_t)(ok ? frame : 0) * PPITCH + f0, ok ? 16 : 0);
@@ -225,14 +228,14 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
             float2 r[16];
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
-                const int n = n1 * 128 + t;
+                const int n = n1 * TF::THREADS + t;
                 r[n1] = n < t_len ? *reinterpret_cast<const float2*>(cur + 4 * n + 2 * pr) : make_float2(0.f, 0.f);
             }
-            fft_stage1(r, tw, s_bufA, t);
+            TF::stage1(r, tw, s_bufA, t);
             __syncthreads();
-            fft_stage2(r, s_bufA, s_bufB, s_tw2, t);
+            TF::stage2(r, s_bufA, s_bufB, s_tw2, t);
             __syncthreads();
-            fft_stage3(r, s_bufB, t);
+            TF::stage3(r, s_bufB, t);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = fmaf(r[i].x, r[i].x, fmaf(r[i].y, r[i].y, acc[i]));
         }
@@ -242,13 +245,13 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int k3 = 0; k3 < 8; ++k3) out[fft_out_column(t, h) + 256 * k3] = acc[h * 8 + k3];
+        for (int k3 = 0; k3 < 8; ++k3) out[TF::out_column(t, h) + TF::CCOLS * k3] = acc[h * 8 + k3];
 }
 
 static size_t beat_smem_bytes(int t_len, int* TP_out) {
     int TP = ((t_len + 7) / 8) * 8 + 8;
     *TP_out = TP;
-    return (size_t)(2 * FFT_BUF + 128) * sizeof(float2) + (size_t)2 * TP * sizeof(float4);
+    return (size_t)(2 * TF::BUF + TF::TW2) * sizeof(float2) + (size_t)2 * TP * sizeof(float4);
 }
 
 void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
@@ -261,7 +264,7 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
         configured = smem;
     }
     dim3 grid(n_parts, n_items * n_seg);
-    k_beat<<<grid, FFT_THREADS, smem, st>>>(P, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part, TP);
+    k_beat<<<grid, TF::THREADS, smem, st>>>(P, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part, TP);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -397,15 +400,16 @@ k_period_certify(const float* __restrict__ P, int T, const int* __restrict__ cer
     for (int t = t_begin + warp; t < t_end; t += 8) {
         const float* __restrict__ a = Pi + (size_t)t * PPITCH;
         const float* __restrict__ b = Pi + (size_t)(t + lag) * PPITCH;
-        float av[33], bv[33];
+        constexpr int DOTN = (NBIN + 31) / 32;
+        float av[DOTN], bv[DOTN];
 #pragma unroll
-        for (int i = 0; i < 33; ++i) {
+        for (int i = 0; i < DOTN; ++i) {
             const int f = lane + 32 * i;
             av[i] = f < NBIN ? __ldg(a + f) : 0.f;
             bv[i] = f < NBIN ? __ldg(b + f) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 33; ++i) acc = fma((double)av[i], (double)bv[i], acc);
+        for (int i = 0; i < DOTN; ++i) acc = fma((double)av[i], (double)bv[i], acc);
     }
     __shared__ double s_red[256];
     s_red[threadIdx.x] = acc;
@@ -454,14 +458,14 @@ void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, 
 // accumulates the cross-spectrum G[k] = conj(A) C over its rows in registers (thread-owned bins
 // k and -k are paired through shared memory) and k_periods inverts sum G once per clip.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FFT_THREADS)
+__global__ void __launch_bounds__(TF::THREADS)
 k_beat_blocked(const float* __restrict__ P, int T, int Bk, int max_lag, FftTables tb, float* __restrict__ g_re,
                float* __restrict__ g_im, int n_fparts, int f_per_part, int TP) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float2* s_bufA = reinterpret_cast<float2*>(s_raw);
-    float2* s_bufB = s_bufA + FFT_BUF;
-    float2* s_tw2 = s_bufB + FFT_BUF;
-    float* s_tile = reinterpret_cast<float*>(s_tw2 + 128);  // [8][TP] rows of P, time contiguous
+    float2* s_bufB = s_bufA + TF::BUF;
+    float2* s_tw2 = s_bufB + TF::BUF;
+    float* s_tile = reinterpret_cast<float*>(s_tw2 + TF::TW2);  // [8][TP] rows of P, time contiguous
     const int t = threadIdx.x;
     const int item = blockIdx.z;
     const int blk = blockIdx.y;
@@ -472,16 +476,16 @@ k_beat_blocked(const float* __restrict__ P, int T, int Bk, int max_lag, FftTable
     const int a_len = min(Bk, T - t0);               // valid frames of a
     const int f_begin = fpart * f_per_part;
     const int f_end = min(NBIN, f_begin + f_per_part);
-    s_tw2[t] = tb.tw2[t];
-    Twiddle1 tw;
-    tw.load(tb.tw1, t);
+    s_tw2[t] = tb.tw2_t[t];
+    TF::Twiddle1 tw;
+    tw.load(tb.tw1_t, t);
     float acc_re[16], acc_im[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc_re[i] = acc_im[i] = 0.f;
     const float* __restrict__ Pitem = P + (size_t)item * T * PPITCH;
     for (int f0 = f_begin; f0 < f_end; f0 += 8) {
         __syncthreads();
-        for (int idx = t; idx < 2 * span; idx += FFT_THREADS) {
+        for (int idx = t; idx < 2 * span; idx += TF::THREADS) {
             const int row = idx >> 1, half = idx & 1;
             float4 v = __ldg(reinterpret_cast<const float4*>(Pitem + (size_t)(t0 + row) * PPITCH + f0 + 4 * half));
             const int f = f0 + 4 * half;
@@ -501,15 +505,15 @@ k_beat_blocked(const float* __restrict__ P, int T, int Bk, int max_lag, FftTable
             const float* __restrict__ col = s_tile + fr * TP;
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
-                const int n = n1 * 128 + t;
+                const int n = n1 * TF::THREADS + t;
                 const float c = n < span ? col[n] : 0.f;
                 r[n1] = make_float2(n < a_len ? c : 0.f, c);
             }
-            fft_stage1(r, tw, s_bufA, t);
+            TF::stage1(r, tw, s_bufA, t);
             __syncthreads();
-            fft_stage2(r, s_bufA, s_bufB, s_tw2, t);
+            TF::stage2(r, s_bufA, s_bufB, s_tw2, t);
             __syncthreads();
-            fft_stage3(r, s_bufB, t);
+            TF::stage3(r, s_bufB, t);
             // Z[k] and Z[-k] are both in this thread's registers (fft_out_column): pair them here
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -535,7 +539,7 @@ k_beat_blocked(const float* __restrict__ P, int T, int Bk, int max_lag, FftTable
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int k3 = 0; k3 < 8; ++k3) {
-            const int k = fft_out_column(t, h) + 256 * k3;
+            const int k = TF::out_column(t, h) + TF::CCOLS * k3;
             g_re[part * BEAT_L + k] = acc_re[h * 8 + k3];
             g_im[part * BEAT_L + k] = acc_im[h * 8 + k3];
         }
@@ -545,14 +549,14 @@ void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, in
                          float* g_re, float* g_im, int n_blocks, int n_fparts, int f_per_part) {
     const int rows = Bk + max_lag - 1;
     const int TP = ((rows + 7) / 8) * 8 + 4;
-    const size_t smem = (size_t)(2 * FFT_BUF + 128) * sizeof(float2) + (size_t)8 * TP * sizeof(float);
+    const size_t smem = (size_t)(2 * TF::BUF + TF::TW2) * sizeof(float2) + (size_t)8 * TP * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(k_beat_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     dim3 grid(n_fparts, n_blocks, n_items);
-    k_beat_blocked<<<grid, FFT_THREADS, smem, st>>>(P, T, Bk, max_lag, tb, g_re, g_im, n_fparts, f_per_part, TP);
+    k_beat_blocked<<<grid, TF::THREADS, smem, st>>>(P, T, Bk, max_lag, tb, g_re, g_im, n_fparts, f_per_part, TP);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -644,8 +648,7 @@ constexpr int MODEL_QB = 8;
 template <int N>
 __device__ __forceinline__ void model_phase(const float2* __restrict__ base, size_t stride, float* __restrict__ out, int t) {
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int k = 2 * (t + 128 * i);
+    for (int k = 2 * t; k < XPITCH; k += 256) {
         const float2 m = strided_median_pair<N>(base + k, stride, k == 0);
         *reinterpret_cast<float2*>(out + k) = m;
     }
@@ -732,12 +735,12 @@ __device__ __forceinline__ float soft_mask(float model, float v2) { return fminf
 // Algorithmic bytes per frame: 16 KB X in, 8 KB audio out (+ model rows, L2 resident).
 // ------------------------------------------------------------------------------------------
 template <int NCH, bool MASKED, int MINB>
-__global__ void __launch_bounds__(FFT_THREADS, MINB)
+__global__ void __launch_bounds__(FF::THREADS, MINB)
 k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ period, int pmax,
              const float* __restrict__ model, int cutoff, float scale, FftTables tb, float* __restrict__ out,
              int nblk) {
-    __shared__ float2 s_buf[2][FFT_BUF];
-    __shared__ float2 s_tw2[128];
+    __shared__ float2 s_buf[2][FF::BUF];
+    __shared__ float2 s_tw2[FF::TW2];
     const int t = threadIdx.x;
     const int item = blockIdx.y;
     const int b0 = blockIdx.x * nblk;               // first output block
@@ -746,7 +749,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     const int n_blocks = g.T + 2 * g.frame_shift - 1;
     const int b1 = min(b0 + nblk, n_blocks);        // one past the last output block
     s_tw2[t] = tb.tw2[t];
-    Twiddle1 tw;
+    FF::Twiddle1 tw;
     tw.load(tb.tw1, t);
     const int gitem = g.item0 + item;
     const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
@@ -779,10 +782,10 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
         }
         // pull the next frame's spectra (NCH x 8 KB) towards L2 while this frame is processed
-        if (jc < b1 && j + 1 < g.T && t < 64 * NCH) prefetch_l2(xl_row + (size_t)(NCH * XPITCH) + t * 16);
+        if (jc < b1 && j + 1 < g.T && t < NCH * (XPITCH / 16)) prefetch_l2(xl_row + (size_t)(NCH * XPITCH) + t * 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int k = t + 128 * i;
+            const int k = t + FF::THREADS * i;
             const float2 xl = __ldg(&xl_row[k]);
             float2 xr = make_float2(0.f, 0.f);
             if (NCH == 2) xr = __ldg(&xr_row[k]);
@@ -799,7 +802,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
                 }
                 // swapped storage: (im, re) of Z = YL + i YR
                 A[0] = make_float2(m_dc_r * xr.x, m_dc_l * xl.x);
-                A[1024] = make_float2(m_ny_r * xr.y, m_ny_l * xl.y);
+                A[XPITCH] = make_float2(m_ny_r * xr.y, m_ny_l * xl.y);
             } else {
                 float m_l = 1.f, m_r = 1.f;
                 if (MASKED) {
@@ -812,17 +815,17 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
                 const float2 yr = make_float2(m_r * xr.x, m_r * xr.y);
                 // Z[k] = YL + i YR ; Z[N-k] = conj(YL) + i conj(YR) ; stored re/im swapped
                 A[k] = make_float2(yl.y + yr.x, yl.x - yr.y);
-                A[2048 - k] = make_float2(yr.x - yl.y, yl.x + yr.y);
+                A[WIN_N - k] = make_float2(yr.x - yl.y, yl.x + yr.y);
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) r[n1] = A[n1 * 128 + t];
-        fft_stage1(r, tw, B, t);
+        for (int n1 = 0; n1 < 16; ++n1) r[n1] = A[n1 * FF::THREADS + t];
+        FF::stage1(r, tw, B, t);
         __syncthreads();
-        fft_stage2(r, B, A, s_tw2, t);
+        FF::stage2(r, B, A, s_tw2, t);
         __syncthreads();
-        fft_stage3(r, A, t);
+        FF::stage3(r, A, t);
         par ^= 1;
         }
         // r[h*8+k3] = (N*yR, N*yL) at frame sample n = (t + 128h) + 256*k3
@@ -832,7 +835,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k3 = 0; k3 < 4; ++k3) {
-                    const long long m = blk + fft_out_column(t, h) + 256 * k3;
+                    const long long m = blk + FF::out_column(t, h) + FF::CCOLS * k3;
                     if (m < g.S) {
                         o0[m] = (carry_l[h * 4 + k3] + r[h * 8 + k3].y) * scale;
                         if (NCH == 2) o1[m] = (carry_r[h * 4 + k3] + r[h * 8 + k3].x) * scale;
@@ -854,7 +857,7 @@ void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const 
     const int nblocks = g.T + 2 * g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
 #define REPET_GO(NCH, MINB) \
-    k_mask_istft<NCH, true, MINB><<<grid, FFT_THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
+    k_mask_istft<NCH, true, MINB><<<grid, FF::THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
     if (nch == 2) {
         if (g_tuning.mask_minb >= 6) REPET_GO(2, 6);
         else if (g_tuning.mask_minb == 5) REPET_GO(2, 5);
@@ -870,9 +873,9 @@ void launch_istft(cudaStream_t st, const float2* X, Geom g, int nch, float scale
     const int nblocks = g.T + 2 * g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
     if (nch == 2)
-        k_mask_istft<2, false, 4><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
+        k_mask_istft<2, false, 4><<<grid, FF::THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
     else
-        k_mask_istft<1, false, 4><<<grid, FFT_THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
+        k_mask_istft<1, false, 4><<<grid, FF::THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -893,7 +896,7 @@ k_mask_only(const float2* __restrict__ X, int T, int nch, const int* __restrict_
 
 void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
                       const float* model, float* mask_out) {
-    dim3 grid(T, 9, n_items * nch);
+    dim3 grid(T, (XPITCH + 128) / 128, n_items * nch);
     k_mask_only<<<grid, 128, 0, st>>>(X, T, nch, period, pmax, model, mask_out);
 }
 

@@ -3,17 +3,40 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Every kernel source is compiled once per supported window length (REPET_WIN_N = 512, 1024, 2048:
+// sampling rates up to 12.8 / 25.6 / 51.2 kHz, repet.py:130) into its own namespace; repet_abi.cu
+// dispatches on repet_params.window_length.  All sizes below are compile-time constants.
+#ifndef REPET_WIN_N
+#define REPET_WIN_N 2048
+#endif
+#define REPET_CAT2(a, b) a##b
+#define REPET_CAT(a, b) REPET_CAT2(a, b)
+#define repet REPET_CAT(repet_w, REPET_WIN_N)
+
+// Launch-shape knobs (repet_set_tuning); defaults are the measured best on B200.  One object for
+// every window-length instantiation (defined in repet_abi.cu).
+struct repet_tuning {
+    int stft_minb = 4;       // resident CTAs per SM the STFT kernel is compiled for (4, 5, 6)
+    int mask_minb = 5;       // same for the mask+ISTFT kernel
+    int frames_per_cta = 0;  // 0 = pick from the batch size
+    int beat_parts = 0;      // 0 = pick from the batch size
+    int cert_rel_ppm = 0;    // period certification window in ppm of the best value (0 = CERT_REL = 100 ppm)
+    int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
+};
+extern repet_tuning g_repet_tuning;
+
 namespace repet {
 
-constexpr int WIN_N = 2048;        // STFT window length supported by this build (fs in (25.6 kHz, 51.2 kHz])
-constexpr int HOP = WIN_N / 2;     // step length H
-constexpr int NBIN = WIN_N / 2 + 1;  // F = 1025 magnitude bins
-constexpr int XPITCH = WIN_N / 2;  // float2 per (frame, channel): bin 0 holds (DC.re, Nyquist.re)
-constexpr int PPITCH = 1032;       // floats per frame row of P / model (1025 rounded up to 32 B)
-constexpr int BEAT_L = 2048;       // FFT length of the beat-spectrum transforms
+constexpr int WIN_N = REPET_WIN_N;   // STFT window length of this compilation
+constexpr int HOP = WIN_N / 2;       // step length H
+constexpr int NBIN = WIN_N / 2 + 1;  // F magnitude bins (1025 at 44.1 kHz)
+constexpr int XPITCH = WIN_N / 2;    // float2 per (frame, channel): bin 0 holds (DC.re, Nyquist.re)
+constexpr int PPITCH = (NBIN + 7) / 8 * 8;  // floats per frame row of P / model (F rounded up to 32 B)
+constexpr int BEAT_L = 2048;         // FFT length of the beat-spectrum transforms (time axis: any window)
 constexpr int MAX_MEDIAN_REGS = 32;  // sorting-network path handles up to 32 gathered values
-constexpr int KPAD = 1056;           // K of the similarity GEMM operand: 1025 zero-padded to 33 x 32 floats
-constexpr int APITCH64 = 1032;       // doubles per row of the float64-normalised frames
+constexpr int KPAD = (NBIN + 31) / 32 * 32;  // K of the similarity GEMM operand: F zero-padded to 32 floats
+constexpr int APITCH64 = PPITCH;     // doubles per row of the float64-normalised frames
+constexpr int FRAME_THREADS = WIN_N / 16;  // threads of one frame transform
 
 // A batch of equally long items cut out of planar audio [clip][channel][sample]:
 // item = clip * seg_per_clip + seg starts at clip*clip_stride + seg*seg_stride (+ c*chan_stride).
@@ -36,22 +59,16 @@ struct Geom {
 };
 
 struct FftTables {
-    const float2* tw1;  // [15][128]  W_2048^(m*k1)
-    const float2* tw2;  // [16][8]    W_128^(m2*k2)
+    const float2* tw1;    // frame transform: [15][N/16]   W_N^(m*k1)
+    const float2* tw2;    //                  [R2][8]      W_(N/16)^(m2*k2)
+    const float2* tw1_t;  // time-axis transform (2048): [15][128]
+    const float2* tw2_t;  //                              [16][8]
 };
 
 enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2 };
 
-// Launch-shape knobs (repet_set_tuning); defaults are the measured best on B200.
-struct Tuning {
-    int stft_minb = 4;       // resident CTAs per SM the STFT kernel is compiled for (4, 5, 6)
-    int mask_minb = 5;       // same for the mask+ISTFT kernel
-    int frames_per_cta = 0;  // 0 = pick from the batch size
-    int beat_parts = 0;      // 0 = pick from the batch size
-    int cert_rel_ppm = 0;    // period certification window in ppm of the best value (0 = CERT_REL = 100 ppm)
-    int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
-};
-extern Tuning g_tuning;
+using Tuning = ::repet_tuning;
+static Tuning& g_tuning = ::g_repet_tuning;
 
 // k_stft: audio -> X (half spectra, both channels) [+ P = (mean_c |X|)^2 or mean_c |X|]
 void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,

@@ -3,7 +3,7 @@
 // (_selfsimilaritymatrix / _similaritymatrix), 1294-1383 (_localmaxima / _indices), 1511-1545
 // (_simmask), 834-901 (the online loop).
 #include "repet_kernels.cuh"
-#include "fft2048.cuh"
+#include "fft_core.cuh"
 #include "median_networks.cuh"
 #include "median_networks_large.cuh"
 
@@ -115,18 +115,20 @@ void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T,
     k_selfsim_simt<<<grid, 256, 0, st>>>(An32, T, S);
 }
 
-// exact float64 dot product of two normalised frames, one warp (result in every lane).  All 33 loads
+constexpr int DOTN = (NBIN + 31) / 32;  // elements of a frame per lane
+
+// exact float64 dot product of two normalised frames, one warp (result in every lane).  All the loads
 // of the global operand are issued before the first multiply so that their latencies overlap.
 __device__ __forceinline__ double warp_dot64(const double* __restrict__ a, const double* __restrict__ b, int lane) {
-    double bv[33];
+    double bv[DOTN];
 #pragma unroll
-    for (int i = 0; i < 33; ++i) {
+    for (int i = 0; i < DOTN; ++i) {
         const int k = lane + 32 * i;
         bv[i] = k < NBIN ? __ldg(b + k) : 0.0;
     }
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 33; ++i) {
+    for (int i = 0; i < DOTN; ++i) {
         const int k = lane + 32 * i;
         if (k < NBIN) s = fma(a[k], bv[i], s);
     }
@@ -366,10 +368,10 @@ k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, d
     // dotted (exact float64) against all the targets it belongs to: u in [j-B+1, j].
     const int u_lo = max(0, j_first - (B - 1)), u_hi = j_first + nf - 1;
     for (int u = u_lo + warp; u <= u_hi; u += nwarp) {
-        double a[33];
+        double a[DOTN];
         const double* __restrict__ row = A + (size_t)u * APITCH64;
 #pragma unroll
-        for (int i = 0; i < 33; ++i) {
+        for (int i = 0; i < DOTN; ++i) {
             const int k = lane + 32 * i;
             a[i] = k < NBIN ? row[k] : 0.0;
         }
@@ -380,7 +382,7 @@ k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, d
             const double* __restrict__ tg = s_tgt + f * APITCH64;
             double s = 0.0;
 #pragma unroll
-            for (int i = 0; i < 33; ++i) {
+            for (int i = 0; i < DOTN; ++i) {
                 const int k = lane + 32 * i;
                 if (k < NBIN) s = fma(a[i], tg[k], s);
             }
@@ -465,10 +467,8 @@ template <int N>
 __device__ __forceinline__ void simmodel_small(const float2* __restrict__ chan, size_t row, const int* __restrict__ list,
                                                float* __restrict__ out, int t) {
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int k = 2 * (t + 128 * i);
+    for (int k = 2 * t; k < XPITCH; k += 256)
         *reinterpret_cast<float2*>(out + k) = gather_median_pair<N>(chan, row, list, k, k == 0);
-    }
     if (t == 0) {
         // Nyquist rides in bin 0's imaginary slot
         float v[N];
@@ -517,7 +517,7 @@ __device__ __forceinline__ float tile_median(float* __restrict__ tile, int n, in
 
 constexpr int SIMMODEL_THREADS = 256;
 
-// squared magnitudes of every (frame, channel) row, [rows][PPITCH]: bin 0 = DC^2, bin 1024 = Nyquist^2.
+// squared magnitudes of every (frame, channel) row, [rows][PPITCH]: bin 0 = DC^2, bin N/2 = Nyquist^2.
 // Long similar-frame lists gather these 4-byte values instead of the 8-byte spectra.
 __global__ void __launch_bounds__(256)
 k_sqmag(const float2* __restrict__ X, long long n_rows, float* __restrict__ Vsq) {
@@ -539,7 +539,7 @@ k_sqmag(const float2* __restrict__ X, long long n_rows, float* __restrict__ Vsq)
 }
 
 void launch_sqmag(cudaStream_t st, const float2* X, long long n_rows, float* Vsq) {
-    dim3 grid((unsigned)n_rows, 5);
+    dim3 grid((unsigned)n_rows, (XPITCH + 256) / 256);
     k_sqmag<<<grid, 256, 0, st>>>(X, n_rows, Vsq);
 }
 
@@ -564,7 +564,7 @@ template <int NS>
 __device__ __forceinline__ void simmodel_large(const float* __restrict__ vchan, size_t vrow, const int* __restrict__ list,
                                                int n, float* __restrict__ out, int t) {
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) out[t + 128 * i] = gather_median_large<NS>(vchan, vrow, list, n, t + 128 * i);
+    for (int k = t; k < XPITCH; k += 128) out[k] = gather_median_large<NS>(vchan, vrow, list, n, k);
     if (t == 0) out[XPITCH] = gather_median_large<NS>(vchan, vrow, list, n, XPITCH);
 }
 
@@ -612,7 +612,7 @@ k_simmodel(const float2* __restrict__ X, const float* __restrict__ Vsq, int T, i
     }
     if (n > 32 && n <= 128) return;  // k_simmodel_large
     if (n <= 32) {
-        // short lists: register selection networks on bin pairs, 128 threads x 4 passes
+        // short lists: register selection networks on bin pairs, 128 threads x 256 bins per pass
         if (t < 128) {
             switch (n) {
 #define REPET_CASE(N) case N: simmodel_small<N>(chan, row, s_list, out, t); break;
@@ -626,13 +626,13 @@ k_simmodel(const float2* __restrict__ X, const float* __restrict__ Vsq, int T, i
         }
         return;
     }
-    // long lists: 4 passes of 256 bins.  The CTA gathers the [n][256] tile of squared magnitudes with
+    // long lists: passes of 256 bins.  The CTA gathers the [n][256] tile of squared magnitudes with
     // 16-byte loads (4 rows per sweep, 8 sweeps in flight per thread), then every thread selects the
     // median of its own column (bank = lane: conflict free) by quickselect.
     const float* __restrict__ vchan = Vsq + ((size_t)item * T * nch + c) * PPITCH;
     const size_t vrow = (size_t)nch * PPITCH;
     const int sub = t >> 6, quad = (t & 63) * 4;  // this thread gathers row (4 s' + sub), bins quad..quad+3
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < XPITCH / 256; ++pass) {
         const int k0 = 256 * pass;
         for (int s0 = 0; s0 < n; s0 += 32) {
             float4 x[8];
@@ -652,7 +652,7 @@ k_simmodel(const float2* __restrict__ X, const float* __restrict__ Vsq, int T, i
         __syncthreads();
     }
     if (t == 0) {
-        // Nyquist^2 sits at bin 1024 of the Vsq rows
+        // Nyquist^2 sits at bin N/2 of the Vsq rows
         for (int s = 0; s < n; ++s) s_tile[s * 256] = __ldg(vchan + (size_t)s_list[s] * vrow + XPITCH);
         out[XPITCH] = tile_median(s_tile, n, 256, 0);
     }

@@ -430,13 +430,20 @@ def period_of(audio_spectrogram, period_range2, handle=None):
     return int(period[0])
 
 
+def _select_bins(handle, number_frequencies):
+    """The mask helpers take whole magnitude spectrograms: F = window_length/2 + 1 selects the
+    library instantiation (the window set last decides, include/repet_b200.h)."""
+    if number_frequencies not in (257, 513, 1025):
+        raise NotImplementedError("spectrograms of 257, 513 or 1025 bins (window_length 512, 1024, 2048) are supported")
+    handle.ensure_window(2 * (number_frequencies - 1))
+
+
 def mask(audio_spectrogram, repeating_period, handle=None):
-    """_mask (repet.py:1386-1458): (1025, T) magnitudes, period -> float64 (1025, T)."""
+    """_mask (repet.py:1386-1458): (F, T) magnitudes, period -> float64 (F, T)."""
     handle = handle or get_handle()
     magnitude = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
     number_times, number_frequencies = magnitude.shape
-    if number_frequencies != 1025:
-        raise NotImplementedError("this build masks 1025-bin spectrograms (window_length 2048)")
+    _select_bins(handle, number_frequencies)
     out = np.empty((number_times, number_frequencies), dtype=np.float32)
     handle.check(handle.lib.repet_mask(handle.h, _ptr(magnitude), number_times, int(repeating_period), _ptr(out)))
     return out.T.astype(np.float64)
@@ -554,12 +561,11 @@ def periods(beat_spectrogram, period_range, handle=None):
 
 
 def adaptivemask(audio_spectrogram, repeating_periods, filter_order, handle=None):
-    """_adaptivemask (repet.py:1461-1508): (1025, T) magnitudes, per-frame periods -> float64 (1025, T)."""
+    """_adaptivemask (repet.py:1461-1508): (F, T) magnitudes, per-frame periods -> float64 (F, T)."""
     handle = handle or get_handle()
     magnitude = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
     number_times, number_frequencies = magnitude.shape
-    if number_frequencies != 1025:
-        raise NotImplementedError("this build masks 1025-bin spectrograms (window_length 2048)")
+    _select_bins(handle, number_frequencies)
     per = np.ascontiguousarray(repeating_periods, dtype=np.int32)
     if per.shape != (number_times,):
         raise ValueError("one period per time frame expected")
@@ -659,12 +665,11 @@ def indices(similarity_matrix, similarity_threshold, similarity_distance, simila
 
 
 def simmask(audio_spectrogram, similarity_indices, handle=None):
-    """_simmask (repet.py:1511-1545): (1025, T) magnitudes + list of index arrays -> float64 (1025, T)."""
+    """_simmask (repet.py:1511-1545): (F, T) magnitudes + list of index arrays -> float64 (F, T)."""
     handle = handle or get_handle()
     magnitude = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)
     number_times, number_frequencies = magnitude.shape
-    if number_frequencies != 1025:
-        raise NotImplementedError("this build masks 1025-bin spectrograms (window_length 2048)")
+    _select_bins(handle, number_frequencies)
     number = max(1, max((len(v) for v in similarity_indices), default=1))
     idx = np.zeros((number_times, number), dtype=np.int32)
     cnt = np.zeros(number_times, dtype=np.int32)

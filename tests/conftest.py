@@ -29,6 +29,12 @@ def golden_drivers():
 
 
 @pytest.fixture(scope="session")
+def golden_rates():
+    """Reference outputs at 8, 16, 22.05 and 48 kHz (window lengths 512, 1024, 2048)."""
+    return dict(np.load(os.path.join(GOLDEN, "drivers_rates.npz")))
+
+
+@pytest.fixture(scope="session")
 def wav_pcm():
     data = np.load(os.path.join(GOLDEN, "audio_file_int16.npz"))
     assert int(data["sampling_frequency"]) == 44100

@@ -103,6 +103,28 @@ def test_driver_vectors(case, fn, golden_drivers, wav_pcm):
         _close(np.concatenate(det["indices"]), g[key + "/index_flat"])
 
 
+RATE_FAST = [(case, fn) for case, spec in make_golden.RATE_CASES.items() for fn in spec["functions"]]
+
+
+@pytest.mark.parametrize("case,fn", RATE_FAST)
+def test_driver_vectors_other_sampling_rates(case, fn, golden_rates):
+    """Window lengths 512 / 1024 and the 48 kHz hop mapping (repet.py:130, quirk Q16)."""
+    warnings.simplefilter("ignore")
+    g = golden_rates
+    spec = make_golden.RATE_CASES[case]
+    x = make_golden.case_input(spec)
+    y, det = getattr(oracle, fn)(x, make_golden.case_fs(spec), return_details=True)
+    key = "%s/%s" % (case, fn)
+    _close(y[:: make_golden.DECIMATE], g[key + "/dec"])
+    if fn == "original":
+        assert det["period"] == int(g[key + "/period"])
+    elif fn in ("extended", "adaptive"):
+        _close(np.asarray(det["periods"]), g[key + "/periods"])
+    elif fn in ("sim", "simonline"):
+        _close(np.array([len(v) for v in det["indices"]]), g[key + "/index_counts"])
+        _close(np.concatenate(det["indices"]), g[key + "/index_flat"])
+
+
 def test_known_answers_cfg1(golden_drivers):
     """The known answers SURVEY.md section 8(c) recorded for BASELINE config 1."""
     g = golden_drivers
