@@ -214,6 +214,75 @@ struct Fft {
             for (int k3 = 0; k3 < 8; ++k3) r[h * 8 + k3] = c[k3];
         }
     }
+
+    // ---- transposed plan (decimation in frequency): the same three radix stages run backwards ----
+    // Input  r[h*8 + k3] = Z[out_column(t, h) + 2T*k3]   (the forward plan's output ownership: a thread
+    //                                                      holds Z[k] and Z[N-k], so Hermitian spectra
+    //                                                      are assembled in registers)
+    // Output r[n1] = x[n1*T + t]                          (samples n and n + N/2 in one thread: the
+    //                                                      overlap-add needs no exchange either)
+    //   tstage3  DFT-8 over k3 of the thread's two columns, times W_T^(m2*k2)        -> y2 layout
+    //   tstage2  DFT-R2 over k2 for (k1 = t%16, m2), times W_N^((n2*8+m2)*k1)        -> y1 layout
+    //   tstage1  DFT-16 over k1 for m = t
+    // Per-thread constant twiddles of tstage2, from the stage-1 table tw1g[(k1-1)*T + m].
+    struct TwiddleT {
+        float2 w[16];
+        __device__ __forceinline__ void load(const float2* __restrict__ tw1g, int t) {
+            const int k1 = t & 15, mb = t >> 4;
+#pragma unroll
+            for (int q = 0; q < NB2; ++q)
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    const int m = n2 * R3 + mb + (THREADS / 16) * q;
+                    w[q * R2 + n2] = k1 ? __ldg(&tw1g[(k1 - 1) * THREADS + m]) : make_float2(1.f, 0.f);
+                }
+        }
+    };
+
+    static __device__ __forceinline__ void tstage3(float2 (&r)[16], float2* __restrict__ dst,
+                                                   const float2* __restrict__ s_tw2, int t) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pi = out_column(t, h);
+            float2 c[8];
+#pragma unroll
+            for (int k3 = 0; k3 < 8; ++k3) c[k3] = r[h * 8 + k3];
+            dft8(c);
+            float2* col = dst + (pi >> 4) * (R3 * 16) + (pi & 15);
+            const float2* twc = s_tw2 + (pi >> 4) * R3;
+            col[0] = c[0];
+#pragma unroll
+            for (int m2 = 1; m2 < 8; ++m2) col[m2 * 16] = cmul(c[m2], twc[m2]);
+        }
+    }
+
+    template <int Q>
+    static __device__ __forceinline__ void tstage2_one(float2 (&r)[16], const float2* __restrict__ src,
+                                                       float2* __restrict__ dst, const TwiddleT& tw, int k1, int mb) {
+        const int m2 = mb + (THREADS / 16) * Q;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) r[Q * R2 + k2] = src[(k2 * R3 + m2) * 16 + k1];
+        dft_slice<R2, Q * R2>(r);
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) dst[k1 * PITCH1 + n2 * R3 + m2] = cmul(r[Q * R2 + n2], tw.w[Q * R2 + n2]);
+    }
+
+    static __device__ __forceinline__ void tstage2(float2 (&r)[16], const float2* __restrict__ src,
+                                                   float2* __restrict__ dst, const TwiddleT& tw, int t) {
+        const int k1 = t & 15, mb = t >> 4;
+        tstage2_one<0>(r, src, dst, tw, k1, mb);
+        if constexpr (NB2 > 1) tstage2_one<(NB2 > 1 ? 1 : 0)>(r, src, dst, tw, k1, mb);
+        if constexpr (NB2 > 2) {
+            tstage2_one<(NB2 > 2 ? 2 : 0)>(r, src, dst, tw, k1, mb);
+            tstage2_one<(NB2 > 2 ? 3 : 0)>(r, src, dst, tw, k1, mb);
+        }
+    }
+
+    static __device__ __forceinline__ void tstage1(float2 (&r)[16], const float2* __restrict__ src, int t) {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) r[k1] = src[k1 * PITCH1 + t];
+        dft16(r);
+    }
 };
 
 // One squared-magnitude / magnitude definition for every kernel, so that |X| is bit-identical

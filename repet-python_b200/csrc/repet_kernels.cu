@@ -720,6 +720,33 @@ void launch_model(cudaStream_t st, const float2* X, int n_items, int T, int nch,
 // computed from the squared magnitude as min(model * rsqrt(V^2), 1): no square root, no division.
 // V = 0 gives model * inf = inf (or NaN for model = 0), and fminf(., 1) returns 1 -- the
 // reference's eps/eps.  For model = 0 < V the reference's eps/(V+eps) ~ 1e-16/V becomes 0.
+// ---- mbarrier / bulk-copy (TMA) primitives for the spectra ring of k_mask_istft ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// one thread: global -> shared bulk copy of `bytes` (multiple of 16), completion on `bar`
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the buffer first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ float soft_mask(float model, float v2) { return fminf(model * fast_rsqrt(v2), 1.0f); }
 
 // ------------------------------------------------------------------------------------------
@@ -734,13 +761,22 @@ __device__ __forceinline__ float soft_mask(float model, float v2) { return fminf
 // MASKED = false is the plain _istft helper.
 // Algorithmic bytes per frame: 16 KB X in, 8 KB audio out (+ model rows, L2 resident).
 // ------------------------------------------------------------------------------------------
+constexpr size_t MASK_ISTFT_SMEM = (size_t)(2 * WIN_N + FF::BUF + FF::TW2) * sizeof(float2) + 2 * sizeof(uint64_t);
+
 template <int NCH, bool MASKED, int MINB>
 __global__ void __launch_bounds__(FF::THREADS, MINB)
 k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ period, int pmax,
              const float* __restrict__ model, int cutoff, float scale, FftTables tb, float* __restrict__ out,
              int nblk) {
-    __shared__ float2 s_buf[2][FF::BUF];
-    __shared__ float2 s_tw2[FF::TW2];
+    // spectra ring: frame f's X rows (NCH x N/2 float2, one bulk copy) land in s_ring[f & 1] while
+    // earlier frames are transformed; once read, the slot doubles as the transform's first exchange
+    // buffer, and it is refilled (two frames ahead) when the second stage has drained it
+    extern __shared__ __align__(128) unsigned char s_dyn[];  // MASK_ISTFT_SMEM bytes (above the static limit at N = 2048)
+    float2(*s_ring)[WIN_N] = reinterpret_cast<float2(*)[WIN_N]>(s_dyn);  // y2 layout and a stereo frame: N float2 each
+    float2* s_y1 = reinterpret_cast<float2*>(s_dyn) + 2 * WIN_N;
+    float2* s_tw2 = s_y1 + FF::BUF;
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tw2 + FF::TW2);
+    constexpr uint32_t ROW_BYTES = NCH * XPITCH * sizeof(float2);
     const int t = threadIdx.x;
     const int item = blockIdx.y;
     const int b0 = blockIdx.x * nblk;               // first output block
@@ -748,8 +784,17 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     // so the last block holds the second half of the last frame alone)
     const int n_blocks = g.T + 2 * g.frame_shift - 1;
     const int b1 = min(b0 + nblk, n_blocks);        // one past the last output block
+    const float2* __restrict__ Xitem = X + (size_t)item * g.T * (size_t)(NCH * XPITCH);
+    // frame jc (centred index) reads row jc - frame_shift; rows outside [first_frame, T) do not exist
+    auto row_of = [&](int jc) { return jc - g.frame_shift; };
+    auto exists = [&](int jc) { return jc <= b1 && row_of(jc) >= g.first_frame && row_of(jc) < g.T; };
+    if (t == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     s_tw2[t] = tb.tw2[t];
-    FF::Twiddle1 tw;
+    typename FF::TwiddleT tw;
     tw.load(tb.tw1, t);
     const int gitem = g.item0 + item;
     const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
@@ -757,99 +802,142 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     float* __restrict__ o1 = o0 + g.chan_stride;
     int p = 1;
     if (MASKED) p = period ? period[item] : pmax;  // no period array: one model row per frame (adaptive, sim)
+    const bool t0 = t == 0;
     float carry_l[8], carry_r[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) carry_l[i] = carry_r[i] = 0.f;
     __syncthreads();
-    int par = 0;
+    if (t == 0) {
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+            if (exists(b0 + d))
+                bulk_load(s_ring[d], Xitem + (size_t)row_of(b0 + d) * (NCH * XPITCH), ROW_BYTES, &s_full[d]);
+    }
+    uint32_t phase = 0;  // bit s = parity of the next completion of slot s
     for (int jc = b0; jc <= b1; ++jc) {
-        const int j = jc - g.frame_shift;  // row of X / of the model
+        const int j = row_of(jc);
+        const int slot = (jc - b0) & 1;
         float2 r[16];
-        if (j < g.first_frame || j >= g.T) {
+        if (!exists(jc)) {
             // a frame that does not exist (online: before the buffer is full): contributes zeros
 #pragma unroll
             for (int i = 0; i < 16; ++i) r[i] = make_float2(0.f, 0.f);
+            if (t == 0 && exists(jc + 2))
+                bulk_load(s_ring[slot], Xitem + (size_t)row_of(jc + 2) * (NCH * XPITCH), ROW_BYTES, &s_full[slot]);
         } else {
-        float2* A = s_buf[par];
-        float2* B = s_buf[par ^ 1];
-        const float2* __restrict__ xl_row = X + ((size_t)item * g.T + j) * (size_t)(NCH * XPITCH);
-        const float2* __restrict__ xr_row = xl_row + XPITCH;
+        // model rows first (L2 resident): their latency hides behind the wait for the spectra
+        float ml[2][4], mr[2][4];
         const float* __restrict__ ml_row = nullptr;
         const float* __restrict__ mr_row = nullptr;
         if (MASKED) {
             const int q = j % p;
             ml_row = model + (((size_t)item * NCH + 0) * pmax + q) * PPITCH;
             mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
-        }
-        // pull the next frame's spectra (NCH x 8 KB) towards L2 while this frame is processed
-        if (jc < b1 && j + 1 < g.T && t < NCH * (XPITCH / 16)) prefetch_l2(xl_row + (size_t)(NCH * XPITCH) + t * 16);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = t + FF::THREADS * i;
-            const float2 xl = __ldg(&xl_row[k]);
-            float2 xr = make_float2(0.f, 0.f);
-            if (NCH == 2) xr = __ldg(&xr_row[k]);
-            if (k == 0) {
-                // DC (mask kept, quirk Q11) and Nyquist, both purely real
-                float m_dc_l = 1.f, m_ny_l = 1.f, m_dc_r = 1.f, m_ny_r = 1.f;
-                if (MASKED) {
-                    m_dc_l = soft_mask(__ldg(&ml_row[0]), xl.x * xl.x);
-                    m_ny_l = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&ml_row[XPITCH]), xl.y * xl.y);
-                    if (NCH == 2) {
-                        m_dc_r = soft_mask(__ldg(&mr_row[0]), xr.x * xr.x);
-                        m_ny_r = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&mr_row[XPITCH]), xr.y * xr.y);
-                    }
-                }
-                // swapped storage: (im, re) of Z = YL + i YR
-                A[0] = make_float2(m_dc_r * xr.x, m_dc_l * xl.x);
-                A[XPITCH] = make_float2(m_ny_r * xr.y, m_ny_l * xl.y);
-            } else {
-                float m_l = 1.f, m_r = 1.f;
-                if (MASKED) {
-                    if (k > cutoff) {
-                        m_l = soft_mask(__ldg(&ml_row[k]), cmag2(xl));
-                        if (NCH == 2) m_r = soft_mask(__ldg(&mr_row[k]), cmag2(xr));
-                    }
-                }
-                const float2 yl = make_float2(m_l * xl.x, m_l * xl.y);
-                const float2 yr = make_float2(m_r * xr.x, m_r * xr.y);
-                // Z[k] = YL + i YR ; Z[N-k] = conj(YL) + i conj(YR) ; stored re/im swapped
-                A[k] = make_float2(yl.y + yr.x, yl.x - yr.y);
-                A[WIN_N - k] = make_float2(yr.x - yl.y, yl.x + yr.y);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) r[n1] = A[n1 * FF::THREADS + t];
-        FF::stage1(r, tw, B, t);
-        __syncthreads();
-        FF::stage2(r, B, A, s_tw2, t);
-        __syncthreads();
-        FF::stage3(r, A, t);
-        par ^= 1;
-        }
-        // r[h*8+k3] = (N*yR, N*yL) at frame sample n = (t + 128h) + 256*k3
-        if (jc > b0) {
-            const long long blk = (long long)(jc - 1) * HOP;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k3 = 0; k3 < 4; ++k3) {
-                    const long long m = blk + FF::out_column(t, h) + FF::CCOLS * k3;
-                    if (m < g.S) {
-                        o0[m] = (carry_l[h * 4 + k3] + r[h * 8 + k3].y) * scale;
-                        if (NCH == 2) o1[m] = (carry_r[h * 4 + k3] + r[h * 8 + k3].x) * scale;
-                    }
+                    const int k = FF::out_column(t, h) + FF::CCOLS * k3;
+                    ml[h][k3] = __ldg(&ml_row[k]);
+                    if (NCH == 2) mr[h][k3] = __ldg(&mr_row[k]);
                 }
         }
+        float2* __restrict__ ring = s_ring[slot];
+        mbar_wait(&s_full[slot], (phase >> slot) & 1u);
+        phase ^= 1u << slot;
+        // The thread masks the 8 bins k < N/2 of its two columns (fft_core.cuh, transposed plan) and
+        // forms Z[k] = YL + i YR and Z[N-k] = conj(YL) + i conj(YR) of the two packed channels, stored
+        // re/im swapped (inverse transform by the forward stages); Z[N-k] lands in its other column.
+        float2 zk[2][4], zm[2][4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+            const int col = FF::out_column(t, h);
 #pragma unroll
             for (int k3 = 0; k3 < 4; ++k3) {
-                carry_l[h * 4 + k3] = r[h * 8 + 4 + k3].y;
-                carry_r[h * 4 + k3] = r[h * 8 + 4 + k3].x;
+                const int k = col + FF::CCOLS * k3;
+                const float2 xl = ring[k];
+                float2 xr = make_float2(0.f, 0.f);
+                if (NCH == 2) xr = ring[XPITCH + k];
+                if (h == 0 && k3 == 0 && t0) {
+                    // bin 0 packs DC (mask kept, quirk Q11) and Nyquist, both purely real
+                    float m_dc_l = 1.f, m_ny_l = 1.f, m_dc_r = 1.f, m_ny_r = 1.f;
+                    if (MASKED) {
+                        m_dc_l = soft_mask(ml[0][0], xl.x * xl.x);
+                        m_ny_l = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&ml_row[XPITCH]), xl.y * xl.y);
+                        if (NCH == 2) {
+                            m_dc_r = soft_mask(mr[0][0], xr.x * xr.x);
+                            m_ny_r = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&mr_row[XPITCH]), xr.y * xr.y);
+                        }
+                    }
+                    zk[h][k3] = make_float2(m_dc_r * xr.x, m_dc_l * xl.x);  // Z[0]
+                    zm[h][k3] = make_float2(m_ny_r * xr.y, m_ny_l * xl.y);  // Z[N/2]
+                } else {
+                    float m_l = 1.f, m_r = 1.f;
+                    if (MASKED) {
+                        if (k > cutoff) {
+                            m_l = soft_mask(ml[h][k3], cmag2(xl));
+                            if (NCH == 2) m_r = soft_mask(mr[h][k3], cmag2(xr));
+                        }
+                    }
+                    const float2 yl = make_float2(m_l * xl.x, m_l * xl.y);
+                    const float2 yr = make_float2(m_r * xr.x, m_r * xr.y);
+                    zk[h][k3] = make_float2(yl.y + yr.x, yl.x - yr.y);
+                    zm[h][k3] = make_float2(yr.x - yl.y, yl.x + yr.y);
+                }
             }
+        }
+        // column t holds bins t + 2T k3, its mirrors sit in column 2T - t at 7 - k3; thread 0 owns the two
+        // self-mirrored columns 0 (mirror 8 - k3, Nyquist at k3 = 4) and T (mirror 7 - k3)
+#pragma unroll
+        for (int k3 = 0; k3 < 4; ++k3) {
+            r[k3] = zk[0][k3];
+            r[8 + k3] = zk[1][k3];
+        }
+        r[4] = t0 ? zm[0][0] : zm[1][3];
+        r[5] = t0 ? zm[0][3] : zm[1][2];
+        r[6] = t0 ? zm[0][2] : zm[1][1];
+        r[7] = t0 ? zm[0][1] : zm[1][0];
+        r[12] = t0 ? zm[1][3] : zm[0][3];
+        r[13] = t0 ? zm[1][2] : zm[0][2];
+        r[14] = t0 ? zm[1][1] : zm[0][1];
+        r[15] = t0 ? zm[1][0] : zm[0][0];
+        __syncthreads();  // every thread has read its spectra: the slot becomes the y2 exchange buffer
+        FF::tstage3(r, ring, s_tw2, t);
+        __syncthreads();
+        FF::tstage2(r, ring, s_y1, tw, t);
+        __syncthreads();  // y2 drained: refill the slot with the frame two ahead
+        if (t == 0 && exists(jc + 2))
+            bulk_load(ring, Xitem + (size_t)row_of(jc + 2) * (NCH * XPITCH), ROW_BYTES, &s_full[slot]);
+        FF::tstage1(r, s_y1, t);
+        }
+        // r[n1] = (N*yR, N*yL) at frame sample n = n1*T + t: n1 < 8 completes block jc - 1, the rest is carried
+        if (jc > b0) {
+            const long long blk = (long long)(jc - 1) * HOP;
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const long long m = blk + n1 * FF::THREADS + t;
+                if (m < g.S) {
+                    o0[m] = (carry_l[n1] + r[n1].y) * scale;
+                    if (NCH == 2) o1[m] = (carry_r[n1] + r[n1].x) * scale;
+                }
+            }
+        }
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            carry_l[n1] = r[8 + n1].y;
+            carry_r[n1] = r[8 + n1].x;
+        }
     }
+}
+
+template <int NCH, bool MASKED, int MINB>
+static void go_mask_istft(cudaStream_t st, dim3 grid, const float2* X, Geom g, const int* period, int pmax,
+                          const float* model, int cutoff, float scale, FftTables tb, float* out, int blocks_per_cta) {
+    // per device, so it is not cached in a static: the call is a few hundred ns
+    cudaFuncSetAttribute(k_mask_istft<NCH, MASKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)MASK_ISTFT_SMEM);
+    k_mask_istft<NCH, MASKED, MINB><<<grid, FF::THREADS, MASK_ISTFT_SMEM, st>>>(X, g, period, pmax, model, cutoff, scale,
+                                                                                  tb, out, blocks_per_cta);
 }
 
 void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const int* period, int pmax,
@@ -857,25 +945,22 @@ void launch_mask_istft(cudaStream_t st, const float2* X, Geom g, int nch, const 
     const int nblocks = g.T + 2 * g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
 #define REPET_GO(NCH, MINB) \
-    k_mask_istft<NCH, true, MINB><<<grid, FF::THREADS, 0, st>>>(X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
+    go_mask_istft<NCH, true, MINB>(st, grid, X, g, period, pmax, model, cutoff, scale, tb, out, blocks_per_cta)
     if (nch == 2) {
-        if (g_tuning.mask_minb >= 6) REPET_GO(2, 6);
-        else if (g_tuning.mask_minb == 5) REPET_GO(2, 5);
+        if (g_tuning.mask_minb >= 5) REPET_GO(2, 5);
+        else if (g_tuning.mask_minb == 3) REPET_GO(2, 3);
         else REPET_GO(2, 4);
     } else {
         REPET_GO(1, 4);
     }
 #undef REPET_GO
 }
-
 void launch_istft(cudaStream_t st, const float2* X, Geom g, int nch, float scale, FftTables tb, float* out,
                   int blocks_per_cta) {
     const int nblocks = g.T + 2 * g.frame_shift - 1;
     dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, g.n_items);
-    if (nch == 2)
-        k_mask_istft<2, false, 4><<<grid, FF::THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
-    else
-        k_mask_istft<1, false, 4><<<grid, FF::THREADS, 0, st>>>(X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
+    if (nch == 2) go_mask_istft<2, false, 4>(st, grid, X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
+    else go_mask_istft<1, false, 4>(st, grid, X, g, nullptr, 0, nullptr, 0, scale, tb, out, blocks_per_cta);
 }
 
 // ------------------------------------------------------------------------------------------

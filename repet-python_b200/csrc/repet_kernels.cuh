@@ -17,7 +17,7 @@
 // every window-length instantiation (defined in repet_abi.cu).
 struct repet_tuning {
     int stft_minb = 4;       // resident CTAs per SM the STFT kernel is compiled for (4, 5, 6)
-    int mask_minb = 5;       // same for the mask+ISTFT kernel
+    int mask_minb = 4;       // same for the mask+ISTFT kernel (3, 4, 5; shared memory allows 4)
     int frames_per_cta = 0;  // 0 = pick from the batch size
     int beat_parts = 0;      // 0 = pick from the batch size
     int cert_rel_ppm = 0;    // period certification window in ppm of the best value (0 = CERT_REL = 100 ppm)
