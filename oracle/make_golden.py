@@ -62,6 +62,46 @@ RATE_CASES = {
 }
 
 
+# a 2-minute track for REPET-SIM (T = 5169 frames, ~394k list entries): long enough that some pairs of
+# similarities are tied to ~1e-8 -- an fp32 analysis front end flips list 3619 -- and the float64 input is
+# deliberately NOT representable in fp32 (1e-9 dither), as a user's array would be.  Stored as per-list
+# counts, one digest per block of 64 lists, and list 3619 in full (sim_long.npz).
+SIM_LONG = dict(index=4242, seconds=120, dither_seed=99, dither=1e-9, block=64, hard_frame=3619)
+
+
+def sim_long_input():
+    x = repet_synth.make_clip(SIM_LONG["index"], SIM_LONG["seconds"] * FS).T.astype(np.float64)
+    rng = np.random.default_rng(SIM_LONG["dither_seed"])
+    return x + SIM_LONG["dither"] * rng.standard_normal(x.shape)
+
+
+def list_digests(lists, block):
+    """uint64 digest of every block of `block` consecutive lists (lengths and contents)."""
+    out = []
+    for lo in range(0, len(lists), block):
+        h = hashlib.sha256()
+        for v in lists[lo : lo + block]:
+            h.update(np.asarray([len(v)], dtype="<i4").tobytes())
+            h.update(np.asarray(v, dtype="<i4").tobytes())
+        out.append(int.from_bytes(h.digest()[:8], "little"))
+    return np.array(out, dtype=np.uint64)
+
+
+def pin_sim_long(ref):
+    x = sim_long_input()
+    N, w, H = oracle.stft_parameters(FS)
+    spec_ref = np.stack([np.abs(ref._stft(x[:, c], w, H)[0 : N // 2 + 1]) for c in range(x.shape[1])], axis=2)
+    lists = ref._indices(ref._selfsimilaritymatrix(np.mean(spec_ref, axis=2)), 0, int(round(FS / H)), 100)
+    out = {
+        "counts": np.array([len(v) for v in lists], dtype=np.uint8),
+        "digests": list_digests(lists, SIM_LONG["block"]),
+        "hard_list": np.asarray(lists[SIM_LONG["hard_frame"]], dtype=np.int32),
+        "total": np.int64(sum(len(v) for v in lists)),
+    }
+    np.savez_compressed(os.path.join(GOLDEN, "sim_long.npz"), **out)
+    print("sim_long: %d lists, %d entries pinned" % (len(lists), int(out["total"])))
+
+
 def case_fs(spec):
     return spec.get("fs", FS)
 
@@ -168,6 +208,9 @@ def main():
         "numpy": np.__version__,
     }
 
+    if "--sim-long-only" in sys.argv:
+        pin_sim_long(ref)
+        return
     # ---- helper-level cases -----------------------------------------------------------
     h = helper_inputs()
     out = {}
@@ -217,6 +260,7 @@ def main():
     for k, v in provenance.items():
         rates["provenance/" + k] = np.array(v)
     np.savez_compressed(os.path.join(GOLDEN, "drivers_rates.npz"), **rates)
+    pin_sim_long(ref)
     sizes = {f: os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN)}
     print("written:", sizes)
 

@@ -113,6 +113,17 @@ int repet_create(int device, repet_handle** out) {
         e = cudaMalloc(&w.tw1, tw1.size() * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&w.tw2, tw2.size() * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&w.window, n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&w.window64, n * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&w.tw64, (n / 2) * sizeof(double2));
+        if (e == cudaSuccess) {
+            std::vector<double2> tw64(n / 2);
+            for (int i = 0; i < n / 2; ++i) {
+                // exact octant symmetries keep cos/sin of the table consistent to the last bit
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)i / (long double)n;
+                tw64[i] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+            e = cudaMemcpy(w.tw64, tw64.data(), tw64.size() * sizeof(double2), cudaMemcpyHostToDevice);
+        }
         if (e == cudaSuccess) e = cudaMemcpy(w.tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(w.tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice);
     }
@@ -134,6 +145,8 @@ int repet_destroy(repet_handle* h) {
         cudaFree(h->win[s].tw1);
         cudaFree(h->win[s].tw2);
         cudaFree(h->win[s].window);
+        cudaFree(h->win[s].window64);
+        cudaFree(h->win[s].tw64);
     }
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -166,6 +179,7 @@ int repet_set_window(repet_handle* h, const double* window, int n) {
     for (int i = 0; i < n; ++i) w[i] = (float)window[i];
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(h->win[slot].window, w.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->win[slot].window64, window, n * sizeof(double), cudaMemcpyHostToDevice));
     h->win[slot].window_set = true;
     h->window_n = n;
     return REPET_OK;
@@ -194,6 +208,7 @@ int repet_set_tuning(const char* name, int value) {
     else if (key == "frames_per_cta") g_repet_tuning.frames_per_cta = value;
     else if (key == "beat_parts") g_repet_tuning.beat_parts = value;
     else if (key == "simgemm_tc") g_repet_tuning.simgemm_tc = value;
+    else if (key == "sim_frames64") g_repet_tuning.sim_frames64 = value;
     else if (key == "cert_rel_ppm") g_repet_tuning.cert_rel_ppm = value;
     else return REPET_E_INVALID_ARG;
     return REPET_OK;

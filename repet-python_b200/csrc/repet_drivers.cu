@@ -316,13 +316,20 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
             geom.first_frame = std::max(0, plan.buffer_frames - 1 - plan.p.online_frame_base);
         }
         const int K = pick_frames_per_cta(h, (long long)g * T);
+        const bool frames64 = g_tuning.sim_frames64 != 0;
         {
             Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, V, P_MAGNITUDE, K);
+            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, frames64 ? nullptr : V, P_MAGNITUDE, K);
         }
         {
             Timed timed(h, REPET_K_NORMALIZE);
-            launch_normalize(st, V, g * T, An64, An32, fast >= 2 ? An32lo : nullptr, fast ? 1 : 0);
+            if (frames64)
+                // the similarity operand comes from a float64 transform of the samples (of the float64 samples
+                // themselves when a *_f64 entry point holds them): integer decisions as in the reference
+                launch_frames64(st, audio, n_clips == 1 ? h->f64_audio : nullptr, geom, nch, h->win[WIN_SLOT].window64,
+                                h->win[WIN_SLOT].tw64, An64, An32, fast >= 2 ? An32lo : nullptr, fast ? 1 : 0);
+            else
+                launch_normalize(st, V, g * T, An64, An32, fast >= 2 ? An32lo : nullptr, fast ? 1 : 0);
         }
         CU(cudaMemsetAsync(cnt, 0, (size_t)g * T * sizeof(int32_t), st));
         if (online) {
@@ -608,7 +615,10 @@ int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nc
         Timed timed(h, REPET_K_CONVERT);
         launch_f64_interleaved_to_planar(st, d64, S, nch, in32);
     }
-    if ((rc = run_plan(h, plan, in32, 1, out32, ints, ws, plan.bytes_per_clip))) return rc;
+    h->f64_audio = d64;
+    rc = run_plan(h, plan, in32, 1, out32, ints, ws, plan.bytes_per_clip);
+    h->f64_audio = nullptr;
+    if (rc) return rc;
     {
         Timed timed(h, REPET_K_CONVERT);
         launch_planar_to_f64_interleaved(st, out32, S, nch, d64);

@@ -23,6 +23,8 @@ struct repet_handle {
         float2* tw1 = nullptr;
         float2* tw2 = nullptr;
         float* window = nullptr;
+        double* window64 = nullptr;  // the same window as given (float64): k_frames64
+        double2* tw64 = nullptr;     // W_N^i, i < N/2, float64: k_frames64
         bool window_set = false;
     } win[3];
     int window_n = 0;  // length of the window set last: what the helper entry points transform with
@@ -31,6 +33,9 @@ struct repet_handle {
     uint64_t ws_limit = 0;
     size_t ws_auto = 0;  // cached automatic workspace limit
     uint64_t launches = 0;
+    // float64 (samples, channels) copy of the clip being separated by a *_f64 entry point, device memory;
+    // the float64 front end of REPET-SIM reads the samples from here instead of their fp32 rounding
+    const double* f64_audio = nullptr;
     int sm_count = 148;
     // optional per-kernel timing (bench.py's roofline): one event pair per launch
     bool profiling = false;

@@ -381,44 +381,60 @@ void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_par
 // When several lags sit within CERT_REL of the maximum of the beat spectrum, the fp32 time-axis
 // transforms of k_beat could flip their order.  Each candidate lag is re-evaluated exactly,
 // b[l] = (1/(T-l)) sum_f sum_t P[f,t] P[f,t+l] accumulated in float64 straight from P (the 1/F factor
-// is common), and the first maximum wins, as np.argmax does.  CTAs of unflagged clips exit at once.
+// is common), and the first maximum wins, as np.argmax does.  Unflagged clips cost one flag read.
 // ------------------------------------------------------------------------------------------
 constexpr int CERT_TSPLIT = 16;  // time chunks per candidate (partial sums are added in a fixed order)
 
 __global__ void __launch_bounds__(256)
-k_period_certify(const float* __restrict__ P, int T, const int* __restrict__ cert, double* __restrict__ cert_part) {
-    const int item = blockIdx.y, slot = blockIdx.x, chunk = blockIdx.z;
-    const int n = cert[item * (CERT_MAX + 1)];
-    if (slot >= n) return;
-    const int lag = cert[item * (CERT_MAX + 1) + 1 + slot];
-    const float* __restrict__ Pi = P + (size_t)item * T * PPITCH;
-    const int rows = T - lag;
-    const int per = (rows + CERT_TSPLIT - 1) / CERT_TSPLIT;
-    const int t_begin = chunk * per, t_end = min(rows, t_begin + per);
+k_period_certify(const float* __restrict__ P, int T, int n_items, const int* __restrict__ cert,
+                 double* __restrict__ cert_part) {
+    // grid = (candidate slot, time chunk, item group): flagged clips are rare, so the CTA first scans the
+    // flags of its group's clips (256 per pass, one per thread) and only walks the ones that need this slot
+    const int slot = blockIdx.x, chunk = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double acc = 0.0;
-    for (int t = t_begin + warp; t < t_end; t += 8) {
-        const float* __restrict__ a = Pi + (size_t)t * PPITCH;
-        const float* __restrict__ b = Pi + (size_t)(t + lag) * PPITCH;
-        constexpr int DOTN = (NBIN + 31) / 32;
-        float av[DOTN], bv[DOTN];
-#pragma unroll
-        for (int i = 0; i < DOTN; ++i) {
-            const int f = lane + 32 * i;
-            av[i] = f < NBIN ? __ldg(a + f) : 0.f;
-            bv[i] = f < NBIN ? __ldg(b + f) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < DOTN; ++i) acc = fma((double)av[i], (double)bv[i], acc);
-    }
+    __shared__ int s_list[256];
+    __shared__ int s_n;
     __shared__ double s_red[256];
-    s_red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    for (int base = blockIdx.z * 256; base < n_items; base += gridDim.z * 256) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const int mine = base + threadIdx.x;
+        if (mine < n_items && cert[mine * (CERT_MAX + 1)] > slot) s_list[atomicAdd(&s_n, 1)] = mine;
+        __syncthreads();
+        const int n_flagged = s_n;
+        for (int q = 0; q < n_flagged; ++q) {
+            const int item = s_list[q];
+            const int lag = cert[item * (CERT_MAX + 1) + 1 + slot];
+            const float* __restrict__ Pi = P + (size_t)item * T * PPITCH;
+            const int rows = T - lag;
+            const int per = (rows + CERT_TSPLIT - 1) / CERT_TSPLIT;
+            const int t_begin = chunk * per, t_end = min(rows, t_begin + per);
+            double acc = 0.0;
+            for (int t = t_begin + warp; t < t_end; t += 8) {
+                const float* __restrict__ a = Pi + (size_t)t * PPITCH;
+                const float* __restrict__ b = Pi + (size_t)(t + lag) * PPITCH;
+                constexpr int DOTN = (NBIN + 31) / 32;
+                float av[DOTN], bv[DOTN];
+#pragma unroll
+                for (int i = 0; i < DOTN; ++i) {
+                    const int f = lane + 32 * i;
+                    av[i] = f < NBIN ? __ldg(a + f) : 0.f;
+                    bv[i] = f < NBIN ? __ldg(b + f) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < DOTN; ++i) acc = fma((double)av[i], (double)bv[i], acc);
+            }
+            s_red[threadIdx.x] = acc;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) cert_part[((size_t)item * CERT_MAX + slot) * CERT_TSPLIT + chunk] = s_red[0];
+            __syncthreads();
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) cert_part[((size_t)item * CERT_MAX + slot) * CERT_TSPLIT + chunk] = s_red[0];
 }
 
 __global__ void k_period_finalize(const int* __restrict__ cert, const double* __restrict__ cert_part, int n_items, int T,
@@ -444,8 +460,8 @@ __global__ void k_period_finalize(const int* __restrict__ cert, const double* __
 
 void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, const int* cert, double* cert_val,
                            int* period) {
-    dim3 grid(CERT_MAX, n_items, CERT_TSPLIT);
-    k_period_certify<<<grid, 256, 0, st>>>(P, T, cert, cert_val);
+    dim3 grid(CERT_MAX, CERT_TSPLIT, (n_items + 255) / 256 < 4 ? (n_items + 255) / 256 : 4);
+    k_period_certify<<<grid, 256, 0, st>>>(P, T, n_items, cert, cert_val);
     k_period_finalize<<<(n_items + 127) / 128, 128, 0, st>>>(cert, cert_val, n_items, T, period);
 }
 

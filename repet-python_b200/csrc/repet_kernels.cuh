@@ -22,6 +22,7 @@ struct repet_tuning {
     int beat_parts = 0;      // 0 = pick from the batch size
     int cert_rel_ppm = 0;    // period certification window in ppm of the best value (0 = CERT_REL = 100 ppm)
     int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
+    int sim_frames64 = 1;    // similarity operand from the float64 front end (k_frames64); 0 = from k_stft's fp32 magnitudes
 };
 extern repet_tuning g_repet_tuning;
 
@@ -125,6 +126,11 @@ void launch_argmax_columns(cudaStream_t st, const double* beat, int n_lags, int 
 // REPET-SIM (repet_sim.cu)
 void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64, float* An32, float* An32lo,
                       int round_tf32);
+// float64 analysis front end of REPET-SIM: audio (fp32 planar, or float64 interleaved of one clip) -> normalised
+// frames An64 and the fast operands rounded from them
+void launch_frames64(cudaStream_t st, const float* audio, const double* audio64, Geom g, int nch,
+                     const double* window64, const double2* tw64, double* An64, float* An32, float* An32lo,
+                     int round_tf32);
 // tcgen05 / TMEM / TMA self-similarity GEMM (repet_simgemm.cu); returns 0 on success
 int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_items, int T, float* S, int sm_count);
 void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);

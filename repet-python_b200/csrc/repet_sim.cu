@@ -58,6 +58,135 @@ void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64,
 }
 
 // ------------------------------------------------------------------------------------------
+// k_frames64  --  float64 analysis front end of REPET-SIM       repet.py:633-667, 1001-1060, 1220
+// A[:, t] = V[:, t] / ||V[:, t]||,  V = mean_c |STFT_c|, computed in float64 from the samples.
+// The similar-frame lists are integers: every decision between two similarities (local-maximum
+// test, threshold, rank) must come out as it does in the reference, which works in float64
+// throughout.  The fp32 transforms of k_stft carry ~1e-7 of relative error into a similarity
+// value -- enough to flip near-tied candidates on a long track -- so the operand of the similarity
+// (An64, and the TF32 operands rounded from it) is rebuilt here with a float64 transform; the fp32
+// spectra of k_stft are only used for the mask and the resynthesis (tolerance 1e-4).
+// One CTA per frame: both channels packed into one complex transform (z = w (xL + i xR)), radix-2
+// Stockham autosort between two shared-memory buffers, Hermitian split, magnitudes by hypot (as
+// np.abs), channel mean, float64 norm, and the three operand formats written in one pass.
+// An all-zero frame gives 0/0 = NaN as in the reference (quirk Q18).
+// ------------------------------------------------------------------------------------------
+constexpr int F64_THREADS = 256;
+
+template <int NCH>
+__global__ void __launch_bounds__(F64_THREADS)
+k_frames64(const float* __restrict__ audio, const double* __restrict__ audio64, Geom g,
+           const double* __restrict__ window64, const double2* __restrict__ tw64, double* __restrict__ An64,
+           float* __restrict__ An32, float* __restrict__ An32lo, int round_tf32) {
+    extern __shared__ __align__(16) unsigned char s_raw64[];
+    double2* bufA = reinterpret_cast<double2*>(s_raw64);
+    double2* bufB = bufA + WIN_N;
+    __shared__ double s_red[F64_THREADS / 32];
+    const int t = threadIdx.x;
+    const int j = blockIdx.x, item = blockIdx.y;
+    const int gitem = g.item0 + item;
+    const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
+    const long long start = g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
+    const long long base = (long long)(j - 1 + g.frame_shift) * HOP;
+    for (int n = t; n < WIN_N; n += F64_THREADS) {
+        const long long idx = base + n;
+        double xl = 0.0, xr = 0.0;
+        if (idx >= 0 && idx < g.S) {
+            if (audio64) {  // float64 (samples, channels) of one clip: the reference's own input
+                xl = audio64[(start + idx) * NCH];
+                if (NCH == 2) xr = audio64[(start + idx) * NCH + 1];
+            } else {
+                xl = (double)audio[start + idx];
+                if (NCH == 2) xr = (double)audio[start + g.chan_stride + idx];
+            }
+        }
+        const double w = window64[n];
+        bufA[n] = make_double2(xl * w, xr * w);
+    }
+    __syncthreads();
+    double2* src = bufA;
+    double2* dst = bufB;
+    for (int ns = 1; ns < WIN_N; ns <<= 1) {
+        const int tw_step = WIN_N / (2 * ns);
+        for (int q = t; q < WIN_N / 2; q += F64_THREADS) {
+            const int k = q & (ns - 1);
+            const double2 w = tw64[k * tw_step];
+            const double2 a = src[q];
+            const double2 b0 = src[q + WIN_N / 2];
+            const double2 b = make_double2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
+            const int o = ((q - k) << 1) + k;
+            dst[o] = make_double2(a.x + b.x, a.y + b.y);
+            dst[o + ns] = make_double2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+        double2* tmp = src;
+        src = dst;
+        dst = tmp;
+    }
+    // src holds Z = FFT(w (xL + i xR)); XL[k] = (Z[k] + conj Z[N-k])/2, XR[k] = (Z[k] - conj Z[N-k])/(2i)
+    double* v = reinterpret_cast<double*>(dst);
+    double sum = 0.0;
+    for (int k = t; k < NBIN; k += F64_THREADS) {
+        const double2 zk = src[k];
+        double mag;
+        if (NCH == 2) {
+            const double2 zm = src[(WIN_N - k) & (WIN_N - 1)];
+            const double ml = hypot(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double mr = hypot(0.5 * (zk.x - zm.x), 0.5 * (zk.y + zm.y));
+            mag = 0.5 * (ml + mr);
+        } else {
+            mag = hypot(zk.x, zk.y);
+        }
+        v[k] = mag;
+        sum = fma(mag, mag, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((t & 31) == 0) s_red[t >> 5] = sum;
+    __syncthreads();
+    double total = 0.0;
+#pragma unroll
+    for (int i = 0; i < F64_THREADS / 32; ++i) total += s_red[i];
+    const double norm = sqrt(total);
+    const size_t row = (size_t)item * g.T + j;
+    for (int k = t; k < KPAD; k += F64_THREADS) {
+        const double a = k < NBIN ? v[k] / norm : 0.0;
+        if (k < APITCH64) An64[row * APITCH64 + k] = a;
+        if (An32) {
+            float f = (float)a;
+            if (round_tf32) {
+                uint32_t bits;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(f));
+                const float hi = __uint_as_float(bits);
+                if (An32lo) {
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"((float)(a - (double)hi)));
+                    An32lo[row * KPAD + k] = __uint_as_float(bits);
+                }
+                f = hi;
+            }
+            An32[row * KPAD + k] = f;
+        }
+    }
+}
+
+void launch_frames64(cudaStream_t st, const float* audio, const double* audio64, Geom g, int nch,
+                     const double* window64, const double2* tw64, double* An64, float* An32, float* An32lo,
+                     int round_tf32) {
+    const size_t smem = (size_t)2 * WIN_N * sizeof(double2);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_frames64<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_frames64<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid(g.T, g.n_items);
+    if (nch == 2)
+        k_frames64<2><<<grid, F64_THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
+    else
+        k_frames64<1><<<grid, F64_THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
+}
+
+// ------------------------------------------------------------------------------------------
 // k_selfsim_simt  --  S = A^T A in fp32 on the CUDA cores (fast pass, error bound tau)
 // 64x64 output tile per CTA, 16x16 threads x 4x4 accumulators, K in chunks of 16 through smem.
 // The products are summed in the same k order for (i, j) and (j, i): S is bitwise symmetric.

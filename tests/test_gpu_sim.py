@@ -148,3 +148,22 @@ def test_streaming_simonline_equals_whole_signal_call(repet):
     assert np.all(streamed[: 430 * 1024] == 0)
     _assert_signal(streamed, whole, "streamed vs whole")
     assert float(np.max(np.abs(streamed - whole))) <= 1e-6 * float(np.max(np.abs(whole)))
+
+
+def test_sim_long_track_lists_match_the_reference(repet):
+    """2-minute track, 5169 lists, float64 input that fp32 cannot hold: every list (set AND order) equals the
+    reference's (tests/golden/sim_long.npz, recorded from the unmodified reference).  The similarity operand
+    comes from the float64 front end; with the fp32 magnitudes of k_stft (sim_frames64 = 0) list 3619 flips
+    on a pair of similarities tied to ~1e-8."""
+    import os
+
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_long.npz"))
+    spec = make_golden.SIM_LONG
+    x = make_golden.sim_long_input()
+    y, lists = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    assert np.array_equal(np.array([len(v) for v in lists]), golden["counts"].astype(np.int64))
+    assert np.array_equal(lists[spec["hard_frame"]], golden["hard_list"])
+    digests = make_golden.list_digests(lists, spec["block"])
+    bad = np.nonzero(digests != golden["digests"])[0]
+    assert bad.size == 0, "lists differ in blocks of %d frames starting at %s" % (spec["block"], (bad * spec["block"]).tolist())
+    assert np.all(np.isfinite(y))

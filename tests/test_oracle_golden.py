@@ -144,3 +144,20 @@ def test_simonline_too_short_raises():
     x = np.zeros((44100 * 5, 2)) + 0.01
     with pytest.raises(ValueError):
         oracle.simonline(x, FS)
+
+
+def test_sim_long_hard_list():
+    """The one list of the 2-minute REPET-SIM track that an fp32 front end gets wrong (two similarities tied
+    to ~1e-8): the float64 oracle reproduces the reference's list for that frame (tests/golden/sim_long.npz)."""
+    import os
+
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_long.npz"))
+    spec = make_golden.SIM_LONG
+    x = make_golden.sim_long_input()
+    N, w, H = oracle.stft_parameters(44100)
+    V = np.mean(np.stack([np.abs(oracle.stft(x[:, c], w, H)[: N // 2 + 1]) for c in range(2)], axis=2), axis=2)
+    assert V.shape[1] == len(golden["counts"])
+    A = V / np.sqrt(np.sum(np.power(V, 2), axis=0))
+    column = np.matmul(A.T, A[:, spec["hard_frame"]])
+    _, idx = oracle.localmaxima(column, 0, int(round(44100 / H)), 100)
+    assert np.array_equal(idx, golden["hard_list"])
