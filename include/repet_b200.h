@@ -89,8 +89,9 @@ const char* repet_version(void);
 #define REPET_K_SIMGEMM 8
 #define REPET_K_TOPK 9
 /* Process-wide launch-shape knobs for experiments: "stft_minb", "mask_minb" (resident CTAs per SM
- * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic), "simgemm_tc" (1 = tcgen05 similarity GEMM, 0 = fp32
- * CUDA-core cross-check kernel). */
+ * the FFT kernels are compiled for: 4, 5, 6), "frames_per_cta", "beat_parts" (0 = automatic), "simgemm_tc" (2 = tcgen05 3xTF32 split
+ * similarity GEMM, 1 = single-pass TF32, 0 = fp32 CUDA-core cross-check kernel), "sim_frames64" (1 = similarity
+ * operand from the float64 front end, 0 = from the fp32 magnitudes), "cert_rel_ppm" (period certification window). */
 int repet_set_tuning(const char* name, int value);
 int repet_set_profiling(repet_handle* h, int on);
 int repet_profile_read(repet_handle* h, double* ms, uint64_t* counts, int reset);
@@ -162,6 +163,27 @@ int repet_simonline_batch(repet_handle* h, const float* audio, int n_clips, int 
                           const repet_params* p, float* background, int32_t* lists_host);
 int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                         double* background, int32_t* lists_host, int lists_capacity);
+
+/* ---- by-products of a separation (README.md:64-81 of the reference) ---------------------- */
+/* One call for the reference's documented usage: background = method(audio) (method 0 original, 1 extended,
+ * 2 adaptive, 3 sim, 4 simonline), foreground = audio - background (README.md:68), and the three display
+ * spectrograms abs(_stft(mean(x, axis=1)))[0:F] of mixture, background and foreground (README.md:79-81),
+ * all from buffers already resident on the device.  float64 (n_samples, n_channels) in and out, HOST
+ * pointers; foreground (optional) like background; spectrograms (optional) fp32
+ * [3][repet_spectrogram_frames][repet_spectrogram_pitch], bins 0..N/2 of every row valid; ints as the
+ * method's own *_f64 entry point. */
+int repet_separate_f64(repet_handle* h, int method, const double* audio, int64_t n_samples, int n_channels,
+                       const repet_params* p, double* background, double* foreground, float* spectrograms,
+                       int32_t* ints_host, int ints_capacity);
+int repet_spectrogram_pitch(const repet_params* p);                     /* floats per spectrogram row: F rounded up to 8 */
+int repet_spectrogram_frames(const repet_params* p, int64_t n_samples); /* repet.py:1018-1028 */
+/* Display spectrogram of every clip of a device-resident batch: audio [n_clips][n_channels][n_samples] fp32 ->
+ * spectrogram [n_clips][frames][pitch] fp32 (device). */
+int repet_spectrogram_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                                const repet_params* p, float* spectrogram);
+/* foreground = audio - background over n_elements fp32 values, device pointers (16-byte aligned). */
+int repet_foreground_dev(repet_handle* h, const float* audio, const float* background, int64_t n_elements,
+                         float* foreground);
 
 /* ---- helpers (unit parity with the reference's private functions), HOST pointers -------- */
 /* _stft (repet.py:1001-1060) of n_channels (1 or 2) real signals at once.

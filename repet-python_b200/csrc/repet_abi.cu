@@ -298,6 +298,31 @@ int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples,
     return dispatch_f64(h, KIND_SIMONLINE, audio, n_samples, n_channels, p, background, lists_host, lists_capacity);
 }
 
+int repet_separate_f64(repet_handle* h, int method, const double* audio, int64_t n_samples, int n_channels,
+                       const repet_params* p, double* background, double* foreground, float* spectrograms,
+                       int32_t* ints_host, int ints_capacity) {
+    const repet_entry* e = entry_for(h, p);
+    if (!e) return h ? (p ? REPET_E_UNSUPPORTED : REPET_E_INVALID_ARG) : REPET_E_INVALID_ARG;
+    if (method < KIND_ORIGINAL || method > KIND_SIMONLINE) return fail(h, REPET_E_INVALID_ARG, "unknown method");
+    return e->separate_f64(h, method, audio, n_samples, n_channels, p, background, foreground, spectrograms, ints_host,
+                           ints_capacity);
+}
+int repet_spectrogram_pitch(const repet_params* p) { return p ? (p->window_length / 2 + 1 + 7) / 8 * 8 : 0; }
+int repet_spectrogram_frames(const repet_params* p, int64_t n_samples) {
+    return (p && p->step_length > 0) ? (int)((n_samples + p->step_length - 1) / p->step_length) + 1 : 0;
+}
+int repet_spectrogram_batch_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                                const repet_params* p, float* spectrogram) {
+    const repet_entry* e = entry_for(h, p);
+    if (!e) return h ? (p ? REPET_E_UNSUPPORTED : REPET_E_INVALID_ARG) : REPET_E_INVALID_ARG;
+    return e->spectrogram_dev(h, audio, n_clips, n_channels, n_samples, p, spectrogram);
+}
+int repet_foreground_dev(repet_handle* h, const float* audio, const float* background, int64_t n_elements,
+                         float* foreground) {
+    if (!h) return REPET_E_INVALID_ARG;
+    return entry_of_slot(2)->foreground_dev(h, audio, background, n_elements, foreground);
+}
+
 // int16 PCM in WAV order [clip][sample][channel] (repet.py:914-947)
 int repet_original_batch_pcm16(repet_handle* h, const int16_t* audio, int n_clips, int n_channels, int64_t n_samples,
                                const repet_params* p, float* background, int32_t* periods_host) {

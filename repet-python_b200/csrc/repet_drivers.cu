@@ -75,7 +75,7 @@ int period_shape(repet_handle* h, const repet_params* p, int nch, int64_t n_samp
 int pick_frames_per_cta(repet_handle* h, long long total_frames) {
     if (g_tuning.frames_per_cta > 0) return g_tuning.frames_per_cta;
     long long k = total_frames / ((long long)h->sm_count * 8);
-    return (int)std::max(4LL, std::min(16LL, k));
+    return (int)std::max(4LL, std::min(24LL, k));  // profiles/r1e_sweep.txt: 24 frames per CTA is the sweet spot
 }
 
 // gin / gout describe ALL items; the pipeline walks them in workspace-sized chunks.
@@ -118,7 +118,7 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
             Timed timed(h, REPET_K_PERIODS);
             launch_periods(st, psd, psd_im, g_items, total_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr,
                            0, periods_dev + first, nullptr, cert);
-            launch_period_certify(st, P, g_items, s.T, cert, cert_val, periods_dev + first);
+            launch_period_certify(st, P, g_items, s.T, 0, s.T, 0, 1, cert, cert_val, periods_dev + first);
         }
         {
             Timed timed(h, REPET_K_MODEL);
@@ -232,6 +232,8 @@ int make_plan(repet_handle* h, int kind, const repet_params* p, int nch, int64_t
         b += align_up((size_t)plan->n_beat_seg * plan->beat_parts * BEAT_L * sizeof(float));
         b += align_up((size_t)plan->n_beat_seg * sizeof(int32_t));
         b += align_up((size_t)nch * plan->T * PPITCH * sizeof(float));
+        b += align_up((size_t)plan->n_beat_seg * (CERT_MAX + 1) * sizeof(int));       // period certification records
+        b += align_up((size_t)plan->n_beat_seg * CERT_MAX * 16 * sizeof(double));
         b += 1024;
         plan->bytes_per_clip = b;
         return REPET_OK;
@@ -441,6 +443,8 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         float* psd = bump.take<float>((size_t)g * plan.n_beat_seg * plan.beat_parts * BEAT_L);
         int32_t* seg_period = bump.take<int32_t>((size_t)g * plan.n_beat_seg);
         float* model = bump.take<float>((size_t)g * nch * T * PPITCH);
+        int* cert = bump.take<int>((size_t)g * plan.n_beat_seg * (CERT_MAX + 1));
+        double* cert_val = bump.take<double>((size_t)g * plan.n_beat_seg * CERT_MAX * 16);  // x CERT_TSPLIT partial sums
         int32_t* frame_period = ints + (size_t)clip0 * T;
         Geom geom = clip_geom(g, nch, plan.S, T);
         geom.first_offset = (long long)clip0 * geom.clip_stride;
@@ -458,7 +462,9 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         {
             Timed timed(h, REPET_K_PERIODS);
             launch_periods(st, psd, nullptr, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
-                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr, nullptr);
+                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr, cert);
+            launch_period_certify(st, P, g * plan.n_beat_seg, T, -plan.left_pad, plan.seg_frames, plan.step_frames,
+                                  plan.n_beat_seg, cert, cert_val, seg_period);
         }
         {
             Timed timed(h, REPET_K_MODEL);
@@ -588,9 +594,34 @@ int batch_host(repet_handle* h, int kind, const void* audio_any, bool pcm16, int
     return REPET_OK;
 }
 
-// float64 (samples, channels) in and out -- the reference's own convention (repet.py:73-77)
+// |STFT(mean_c x)|[0:F] of every clip (the display spectrogram of README.md:79-81), device resident:
+// spectrogram [n_clips][T][PPITCH] fp32
+int spectrogram_dev(repet_handle* h, const float* audio, int n_clips, int nch, int64_t S, const repet_params* p,
+                    float* spectrogram) {
+    int rc = check_common(h, p, nch);
+    if (rc) return rc;
+    if (!audio || !spectrogram || n_clips < 0 || S < 1) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    if (S > 2147483647LL - 4096) return fail(h, REPET_E_UNSUPPORTED, "more than 2^31 samples per clip");
+    CU(cudaSetDevice(h->device));
+    const int T = frames_of(S);
+    for (int first = 0; first < n_clips; first += MAX_ITEMS_PER_LAUNCH) {
+        Geom g = clip_geom(std::min(MAX_ITEMS_PER_LAUNCH, n_clips - first), nch, S, T);
+        g.first_offset = (long long)first * g.clip_stride;
+        Timed timed(h, REPET_K_STFT);
+        launch_stft(h->stream, audio, g, nch, window_of(h), tables(h), nullptr, spectrogram + (size_t)first * T * PPITCH,
+                    P_MIXDOWN, pick_frames_per_cta(h, (long long)g.n_items * T));
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+// float64 (samples, channels) in and out -- the reference's own convention (repet.py:73-77).
+// Optional by-products of the buffers already resident (README.md:64-81): the foreground
+// (audio - background) and the display spectrograms of mixture, background and foreground,
+// spectrograms [3][T][PPITCH] fp32 on the host.
 int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nch, const repet_params* p,
-               double* background, int32_t* ints_host, int ints_capacity) {
+               double* background, int32_t* ints_host, int ints_capacity, double* foreground = nullptr,
+               float* spectrograms = nullptr) {
     int rc = check_common(h, p, nch);
     if (rc) return rc;
     if (!audio || !background || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
@@ -600,14 +631,18 @@ int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nc
     if (ints_host && ints_capacity < plan.ints_per_clip)
         return fail(h, REPET_E_INVALID_ARG, "integer output buffer too small");
     const size_t n = (size_t)S * nch;
+    const int T_spec = frames_of(S);
+    const size_t spec_elems = spectrograms ? (size_t)3 * T_spec * PPITCH : 0;
     const size_t need = align_up((size_t)plan.ints_per_clip * sizeof(int32_t)) + align_up(n * sizeof(double)) +
-                        2 * align_up(n * sizeof(float)) + plan.bytes_per_clip;
+                        3 * align_up(n * sizeof(float)) + align_up(spec_elems * sizeof(float)) + plan.bytes_per_clip;
     if ((rc = ensure_arena(h, need))) return rc;
     Bump bump(h->arena);
     int32_t* ints = bump.take<int32_t>(plan.ints_per_clip);
     double* d64 = bump.take<double>(n);
     float* in32 = bump.take<float>(n);
     float* out32 = bump.take<float>(n);
+    float* fg32 = bump.take<float>(n);
+    float* spec = bump.take<float>(spec_elems);
     unsigned char* ws = h->arena + bump.off;
     cudaStream_t st = h->stream;
     CU(cudaMemcpyAsync(d64, audio, n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -619,11 +654,27 @@ int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nc
     rc = run_plan(h, plan, in32, 1, out32, ints, ws, plan.bytes_per_clip);
     h->f64_audio = nullptr;
     if (rc) return rc;
+    if (foreground || spectrograms) {
+        Timed timed(h, REPET_K_CONVERT);
+        launch_foreground(st, in32, out32, (long long)n, fg32);
+    }
+    if (spectrograms) {
+        const float* sources[3] = {in32, out32, fg32};
+        for (int i = 0; i < 3; ++i)
+            if ((rc = spectrogram_dev(h, sources[i], 1, nch, S, p, spec + (size_t)i * T_spec * PPITCH))) return rc;
+        CU(cudaMemcpyAsync(spectrograms, spec, spec_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     {
         Timed timed(h, REPET_K_CONVERT);
         launch_planar_to_f64_interleaved(st, out32, S, nch, d64);
     }
     CU(cudaMemcpyAsync(background, d64, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (foreground) {
+        // stream order: the copy above has read d64 before it is overwritten
+        Timed timed(h, REPET_K_CONVERT);
+        launch_planar_to_f64_interleaved(st, fg32, S, nch, d64);
+        CU(cudaMemcpyAsync(foreground, d64, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (ints_host)
         CU(cudaMemcpyAsync(ints_host, ints, (size_t)plan.ints_per_clip * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -646,6 +697,26 @@ int drv_single_f64(repet_handle* h, int kind, const double* audio, int64_t n_sam
                    const repet_params* p, double* background, int32_t* ints, int64_t ints_capacity) {
     return single_f64(h, kind, audio, n_samples, n_channels, p, background, ints,
                       (int)std::min<int64_t>(ints_capacity, INT32_MAX));
+}
+int drv_separate_f64(repet_handle* h, int kind, const double* audio, int64_t n_samples, int n_channels,
+                     const repet_params* p, double* background, double* foreground, float* spectrograms, int32_t* ints,
+                     int64_t ints_capacity) {
+    return single_f64(h, kind, audio, n_samples, n_channels, p, background, ints,
+                      (int)std::min<int64_t>(ints_capacity, INT32_MAX), foreground, spectrograms);
+}
+int drv_spectrogram_dev(repet_handle* h, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                        const repet_params* p, float* spectrogram) {
+    return spectrogram_dev(h, audio, n_clips, n_channels, n_samples, p, spectrogram);
+}
+int drv_foreground_dev(repet_handle* h, const float* audio, const float* background, int64_t n, float* foreground) {
+    if (!h || !audio || !background || !foreground || n < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    if (((uintptr_t)audio | (uintptr_t)background | (uintptr_t)foreground) & 15)
+        return fail(h, REPET_E_INVALID_ARG, "buffers must be 16-byte aligned");
+    CU(cudaSetDevice(h->device));
+    Timed timed(h, REPET_K_CONVERT);
+    launch_foreground(h->stream, audio, background, (long long)n, foreground);
+    CU(cudaGetLastError());
+    return REPET_OK;
 }
 
 }  // namespace repet

@@ -69,6 +69,13 @@ struct repet_entry {
     int (*localmaxima)(repet_handle*, const double*, int, int, double, int, int, int32_t*, int32_t*, double*);
     int (*simmask)(repet_handle*, const float*, int, const int32_t*, const int32_t*, int, float*);
     int (*acorr)(repet_handle*, const float*, int, int, double*);
+    // by-products (README.md:64-81)
+    int (*separate_f64)(repet_handle*, int kind, const double* audio, int64_t n_samples, int n_channels,
+                        const repet_params* p, double* background, double* foreground, float* spectrograms,
+                        int32_t* ints, int64_t ints_capacity);
+    int (*spectrogram_dev)(repet_handle*, const float* audio, int n_clips, int n_channels, int64_t n_samples,
+                           const repet_params* p, float* spectrogram);
+    int (*foreground_dev)(repet_handle*, const float* audio, const float* background, int64_t n, float* foreground);
 };
 
 namespace repet {

@@ -42,7 +42,20 @@ __device__ __forceinline__ void stft_emit(float2 a, float2 b, int k, float2* __r
     if (prow) prow[k] = pmode == P_POWER ? mean * mean : mean;
 }
 
-template <int NCH, int MINB>
+// display spectrogram |STFT(mean_c x)| (README.md:79-81): the transform is linear, so the STFT of the channel
+// mean is the mean of the channel spectra; only the magnitude row is written
+template <int NCH>
+__device__ __forceinline__ void stft_emit_mixdown(float2 a, float2 b, int k, float* __restrict__ prow) {
+    const float2 xl = __ffma2_rn(b, make_float2(1.f, -1.f), a);
+    if (NCH == 2) {
+        const float2 d = __ffma2_rn(b, make_float2(-1.f, 1.f), a);  // XR = (d.y, -d.x)
+        prow[k] = 0.5f * cmag(make_float2(xl.x + d.y, xl.y - d.x));
+    } else {
+        prow[k] = cmag(xl);
+    }
+}
+
+template <int NCH, int MINB, bool MIXDOWN = false>
 __global__ void __launch_bounds__(FF::THREADS, MINB)
 k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window, FftTables tb,
        float2* __restrict__ X, float* __restrict__ P, int pmode, int K) {
@@ -118,6 +131,24 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
         float2* __restrict__ xrow = X + frame * (size_t)(NCH * XPITCH);
         float* __restrict__ prow = P ? P + frame * (size_t)PPITCH : nullptr;
         if (prow && t >= 1 && t < PPITCH - XPITCH) prow[XPITCH + t] = 0.f;  // rows 1025..1031: zero padding
+        if (MIXDOWN) {
+            if (t != 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int k3 = 0; k3 < 4; ++k3)
+                        stft_emit_mixdown<NCH>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3], (h == 0 ? t : FF::CCOLS - t) + FF::CCOLS * k3, prow);
+            } else {
+                const float2 dc = r[0], ny = r[4];
+                prow[0] = NCH == 2 ? fabsf(dc.x + dc.y) : 2.f * fabsf(dc.x);
+                prow[XPITCH] = NCH == 2 ? fabsf(ny.x + ny.y) : 2.f * fabsf(ny.x);
+#pragma unroll
+                for (int k3 = 1; k3 < 4; ++k3) stft_emit_mixdown<NCH>(r[k3], r[8 - k3], FF::CCOLS * k3, prow);
+#pragma unroll
+                for (int k3 = 0; k3 < 4; ++k3) stft_emit_mixdown<NCH>(r[8 + k3], r[8 + 7 - k3], FF::THREADS + FF::CCOLS * k3, prow);
+            }
+            continue;
+        }
         if (t != 0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -148,6 +179,11 @@ void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const flo
                  float* P, int pmode, int frames_per_cta) {
     dim3 grid((g.T + frames_per_cta - 1) / frames_per_cta, g.n_items);
 #define REPET_GO(NCH, MINB) k_stft<NCH, MINB><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta)
+    if (pmode == P_MIXDOWN) {  // spectrogram only: X is not written
+        if (nch == 2) k_stft<2, 4, true><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, nullptr, P, pmode, frames_per_cta);
+        else k_stft<1, 4, true><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, nullptr, P, pmode, frames_per_cta);
+        return;
+    }
     if (nch == 2) {
         if (g_tuning.stft_minb >= 6) REPET_GO(2, 6);
         else if (g_tuning.stft_minb == 5) REPET_GO(2, 5);
@@ -314,7 +350,33 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
     }
     for (int l = l0 + t; l < l1; l += 256) {
         double s = 0.0;
-        if (psd_part_im) {
+        if (!beat_out) {
+            // period search only: Clenshaw's recurrence for sum_k a_k cos(k theta) (and b_1 sin(theta) for the
+            // sine series) -- one broadcast load and one dependent DFMA per term instead of a table lookup with
+            // lane-dependent stride.  Its rounding (~1e-12 relative for the lags in range) is far inside the
+            // 100 ppm window below which k_period_certify re-decides the argmax from exact sums.
+            double sn, c;
+            sincospi((double)l / (double)(BEAT_L / 2), &sn, &c);
+            const double c2 = 2.0 * c;
+            double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
+            if (psd_part_im) {
+                for (int k = BEAT_L / 2 - 1; k >= 1; --k) {
+                    const double b0 = fma(c2, b1, s_psd[k] - b2);
+                    const double d0 = fma(c2, d1, s_im[k] - d2);
+                    b2 = b1;
+                    b1 = b0;
+                    d2 = d1;
+                    d1 = d0;
+                }
+            } else {
+                for (int k = BEAT_L / 2 - 1; k >= 1; --k) {
+                    const double b0 = fma(c2, b1, s_psd[k] - b2);
+                    b2 = b1;
+                    b1 = b0;
+                }
+            }
+            s = fma(b1, c, -b2) - d1 * sn;
+        } else if (psd_part_im) {
             for (int k = 1; k < BEAT_L / 2; ++k) {
                 const int ph = (k * l) & (BEAT_L - 1);
                 s = fma(s_psd[k], s_cos[ph], s);
@@ -346,11 +408,27 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
         }
         period[bi] = arg + 1;
         if (cert) {
-            // lags whose value is within CERT_REL of the best: k_period_certify re-evaluates them exactly
+            // lags whose value is within CERT_REL of the best: k_period_certify re-evaluates them exactly.
+            // If more than CERT_MAX qualify the CERT_MAX largest are kept (the maximum is always among
+            // them); they are stored in ascending lag order, which the first-maximum rule relies on.
             int n = 0;
+            int lags[CERT_MAX];
             const double floor_v = best - fabs(best) * cert_rel;
-            for (int l = lag_lo; l < lag_hi && n < CERT_MAX; ++l)
-                if (s_b[l] >= floor_v) cert[bi * (CERT_MAX + 1) + 1 + n++] = l;
+            for (int l = lag_lo; l < lag_hi; ++l) {
+                if (!(s_b[l] >= floor_v)) continue;
+                if (n < CERT_MAX) {
+                    lags[n++] = l;
+                } else {
+                    int weakest = 0;
+                    for (int q = 1; q < CERT_MAX; ++q)
+                        if (s_b[lags[q]] < s_b[lags[weakest]]) weakest = q;
+                    if (s_b[l] > s_b[lags[weakest]]) {  // drop the weakest, keep ascending order
+                        for (int q = weakest; q + 1 < CERT_MAX; ++q) lags[q] = lags[q + 1];
+                        lags[CERT_MAX - 1] = l;
+                    }
+                }
+            }
+            for (int q = 0; q < n; ++q) cert[bi * (CERT_MAX + 1) + 1 + q] = lags[q];
             cert[bi * (CERT_MAX + 1)] = n >= 2 ? n : 0;
         }
         if (stats) {
@@ -380,65 +458,71 @@ void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_par
 // k_period_certify / k_period_finalize  --  near-tied period candidates decided in float64
 // When several lags sit within CERT_REL of the maximum of the beat spectrum, the fp32 time-axis
 // transforms of k_beat could flip their order.  Each candidate lag is re-evaluated exactly,
-// b[l] = (1/(T-l)) sum_f sum_t P[f,t] P[f,t+l] accumulated in float64 straight from P (the 1/F factor
+// b[l] = (1/(R-l)) sum_f sum_t P[f,t] P[f,t+l] (R rows of the clip or of the adaptive segment, zero outside the
+// clip) accumulated in float64 straight from P (the 1/F factor
 // is common), and the first maximum wins, as np.argmax does.  Unflagged clips cost one flag read.
 // ------------------------------------------------------------------------------------------
 constexpr int CERT_TSPLIT = 16;  // time chunks per candidate (partial sums are added in a fixed order)
 
+constexpr int CERT_GROUP = 32;   // beat items whose flags one CTA scans (one per lane of warp 0)
+
 __global__ void __launch_bounds__(256)
-k_period_certify(const float* __restrict__ P, int T, int n_items, const int* __restrict__ cert,
-                 double* __restrict__ cert_part) {
-    // grid = (candidate slot, time chunk, item group): flagged clips are rare, so the CTA first scans the
-    // flags of its group's clips (256 per pass, one per thread) and only walks the ones that need this slot
+k_period_certify(const float* __restrict__ P, int T, int n_items, int t_first, int t_len, int seg_step, int n_seg,
+                 const int* __restrict__ cert, double* __restrict__ cert_part) {
+    // grid = (candidate slot, time chunk, group of 32 beat items): flagged items are rare, so the CTA reads
+    // the 32 flags of its group at once and only walks the items that need this slot
     const int slot = blockIdx.x, chunk = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ int s_list[256];
-    __shared__ int s_n;
-    __shared__ double s_red[256];
-    for (int base = blockIdx.z * 256; base < n_items; base += gridDim.z * 256) {
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-        const int mine = base + threadIdx.x;
-        if (mine < n_items && cert[mine * (CERT_MAX + 1)] > slot) s_list[atomicAdd(&s_n, 1)] = mine;
-        __syncthreads();
-        const int n_flagged = s_n;
-        for (int q = 0; q < n_flagged; ++q) {
-            const int item = s_list[q];
-            const int lag = cert[item * (CERT_MAX + 1) + 1 + slot];
-            const float* __restrict__ Pi = P + (size_t)item * T * PPITCH;
-            const int rows = T - lag;
-            const int per = (rows + CERT_TSPLIT - 1) / CERT_TSPLIT;
-            const int t_begin = chunk * per, t_end = min(rows, t_begin + per);
-            double acc = 0.0;
-            for (int t = t_begin + warp; t < t_end; t += 8) {
-                const float* __restrict__ a = Pi + (size_t)t * PPITCH;
-                const float* __restrict__ b = Pi + (size_t)(t + lag) * PPITCH;
-                constexpr int DOTN = (NBIN + 31) / 32;
-                float av[DOTN], bv[DOTN];
+    __shared__ unsigned s_flags;
+    __shared__ double s_red[8];
+    if (warp == 0) {
+        const int mine = blockIdx.z * CERT_GROUP + lane;
+        const unsigned flags = __ballot_sync(0xffffffffu, mine < n_items && cert[mine * (CERT_MAX + 1)] > slot);
+        if (lane == 0) s_flags = flags;
+    }
+    __syncthreads();
+    unsigned flags = s_flags;
+    while (flags) {
+        const int item = blockIdx.z * CERT_GROUP + __ffs(flags) - 1;
+        flags &= flags - 1;
+        const int lag = cert[item * (CERT_MAX + 1) + 1 + slot];
+        // beat item = (clip, segment): rows [ts, ts + t_len) of the clip's P, zero outside [0, T)
+        const int clip = item / n_seg, ts = t_first + (item - clip * n_seg) * seg_step;
+        const float* __restrict__ Pi = P + (size_t)clip * T * PPITCH;
+        const int rows = t_len - lag;
+        const int per = (rows + CERT_TSPLIT - 1) / CERT_TSPLIT;
+        const int t_begin = max(ts + chunk * per, 0), t_end = min(ts + min(rows, (chunk + 1) * per), T - lag);
+        double acc = 0.0;
+        for (int t = t_begin + warp; t < t_end; t += 8) {
+            const float* __restrict__ a = Pi + (size_t)t * PPITCH;
+            const float* __restrict__ b = Pi + (size_t)(t + lag) * PPITCH;
+            constexpr int DOTN = (NBIN + 31) / 32;
+            float av[DOTN], bv[DOTN];
 #pragma unroll
-                for (int i = 0; i < DOTN; ++i) {
-                    const int f = lane + 32 * i;
-                    av[i] = f < NBIN ? __ldg(a + f) : 0.f;
-                    bv[i] = f < NBIN ? __ldg(b + f) : 0.f;
-                }
+            for (int i = 0; i < DOTN; ++i) {
+                const int f = lane + 32 * i;
+                av[i] = f < NBIN ? __ldg(a + f) : 0.f;
+                bv[i] = f < NBIN ? __ldg(b + f) : 0.f;
+            }
 #pragma unroll
-                for (int i = 0; i < DOTN; ++i) acc = fma((double)av[i], (double)bv[i], acc);
-            }
-            s_red[threadIdx.x] = acc;
-            __syncthreads();
-            for (int o = 128; o > 0; o >>= 1) {
-                if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) cert_part[((size_t)item * CERT_MAX + slot) * CERT_TSPLIT + chunk] = s_red[0];
-            __syncthreads();
+            for (int i = 0; i < DOTN; ++i) acc = fma((double)av[i], (double)bv[i], acc);
+        }
+        // fixed-order reduction: lanes by butterfly, then the 8 warps in order
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double total = 0.0;
+            for (int w = 0; w < 8; ++w) total += s_red[w];
+            cert_part[((size_t)item * CERT_MAX + slot) * CERT_TSPLIT + chunk] = total;
         }
         __syncthreads();
     }
 }
 
-__global__ void k_period_finalize(const int* __restrict__ cert, const double* __restrict__ cert_part, int n_items, int T,
-                                  int* __restrict__ period) {
+__global__ void k_period_finalize(const int* __restrict__ cert, const double* __restrict__ cert_part, int n_items,
+                                  int t_len, int* __restrict__ period) {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n_items) return;
     const int n = cert[item * (CERT_MAX + 1)];
@@ -449,7 +533,7 @@ __global__ void k_period_finalize(const int* __restrict__ cert, const double* __
         const int lag = cert[item * (CERT_MAX + 1) + 1 + s];
         double v = 0.0;
         for (int c = 0; c < CERT_TSPLIT; ++c) v += cert_part[((size_t)item * CERT_MAX + s) * CERT_TSPLIT + c];
-        v /= (double)(T - lag);
+        v /= (double)(t_len - lag);
         if (arg < 0 || v > best) {  // candidates are in ascending lag order: strict > keeps the first maximum
             best = v;
             arg = lag;
@@ -458,11 +542,11 @@ __global__ void k_period_finalize(const int* __restrict__ cert, const double* __
     period[item] = arg + 1;
 }
 
-void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, const int* cert, double* cert_val,
-                           int* period) {
-    dim3 grid(CERT_MAX, CERT_TSPLIT, (n_items + 255) / 256 < 4 ? (n_items + 255) / 256 : 4);
-    k_period_certify<<<grid, 256, 0, st>>>(P, T, n_items, cert, cert_val);
-    k_period_finalize<<<(n_items + 127) / 128, 128, 0, st>>>(cert, cert_val, n_items, T, period);
+void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step,
+                           int n_seg, const int* cert, double* cert_val, int* period) {
+    dim3 grid(CERT_MAX, CERT_TSPLIT, (n_items + CERT_GROUP - 1) / CERT_GROUP);
+    k_period_certify<<<grid, 256, 0, st>>>(P, T, n_items, t_first, t_len, seg_step, n_seg, cert, cert_val);
+    k_period_finalize<<<(n_items + 127) / 128, 128, 0, st>>>(cert, cert_val, n_items, t_len, period);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1198,6 +1282,23 @@ __global__ void k_pcm16_to_planar(const int16_t* __restrict__ in, long long S, i
 void launch_pcm16_to_planar(cudaStream_t st, const int16_t* in, int n_clips, long long S, int C, float* out) {
     dim3 grid((unsigned)((S + 255) / 256), n_clips);
     k_pcm16_to_planar<<<grid, 256, 0, st>>>(in, S, C, out);
+}
+
+// foreground = audio - background (README.md:68), 16 bytes per thread, tail by the last threads
+__global__ void k_foreground(const float* __restrict__ audio, const float* __restrict__ background, long long n,
+                             float* __restrict__ foreground) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 a = *reinterpret_cast<const float4*>(audio + i);
+        const float4 b = *reinterpret_cast<const float4*>(background + i);
+        *reinterpret_cast<float4*>(foreground + i) = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    } else {
+        for (long long k = i; k < n; ++k) foreground[k] = audio[k] - background[k];
+    }
+}
+void launch_foreground(cudaStream_t st, const float* audio, const float* background, long long n, float* foreground) {
+    const long long threads = (n + 3) / 4;
+    if (threads > 0) k_foreground<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(audio, background, n, foreground);
 }
 
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out) {

@@ -66,7 +66,7 @@ struct FftTables {
     const float2* tw2_t;  //                              [16][8]
 };
 
-enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2 };
+enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2, P_MIXDOWN = 3 };  // MIXDOWN: |STFT(mean_c x)| only, no X
 
 using Tuning = ::repet_tuning;
 static Tuning& g_tuning = ::g_repet_tuning;
@@ -87,8 +87,9 @@ void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_par
 // near-tied period candidates re-decided in float64 (cert: [item][1 + CERT_MAX] ints written by k_periods)
 constexpr int CERT_MAX = 8;
 constexpr double CERT_REL = 1e-4;
-void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, const int* cert, double* cert_val,
-                           int* period);
+// n_items beat items = clips x n_seg segments of rows [t_first + seg*seg_step, ... + t_len) (original: 0, T, 0, 1)
+void launch_period_certify(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step,
+                           int n_seg, const int* cert, double* cert_val, int* period);
 // k_beat_blocked: clips longer than one transform, complex cross-spectrum partials
 // g_re / g_im [item][block][fpart][2048]
 void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, int Bk, int max_lag, FftTables tb,
@@ -147,6 +148,9 @@ int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_it
 void launch_cosine64(cudaStream_t st, const double* A1, int n1, const double* A2, int n2, double* out);
 int launch_localmaxima64(cudaStream_t st, const double* data, int n, int n_columns, double thr, int d, int number,
                          int* idx_out, int* cnt_out, double* val_out);
+
+// foreground = audio - background, any layout (n fp32 elements; 16-byte aligned pointers)
+void launch_foreground(cudaStream_t st, const float* audio, const float* background, long long n, float* foreground);
 
 // layout converters for the float64 (S, C) NumPy convention of the reference API
 void launch_pcm16_to_planar(cudaStream_t st, const int16_t* in, int n_clips, long long S, int C, float* out);

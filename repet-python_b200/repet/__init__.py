@@ -20,7 +20,9 @@ Other:
     wavwrite - Write a WAVE file (using SciPy).
     specshow - Display an spectrogram in dB, seconds, and Hz.
 
-Beyond the reference: `original_batch` for many clips per call.
+Beyond the reference: `*_batch` for many clips per call, `SimOnline` for block-wise
+streaming, `separate` (background + foreground + the three display spectrograms of README.md:64-81 in one
+device pass), `spectrogram` and `spectrogram_db`.
 """
 
 import numpy as np
@@ -140,6 +142,35 @@ def simonline(audio_signal, sampling_frequency):
     return _host.simonline_f64(audio_signal, sampling_frequency, _tunables())
 
 
+def separate(audio_signal, sampling_frequency, method="original", spectrograms=True):
+    """
+    The documented usage of the reference in one call (README.md:64-81): estimate the background with
+    `method` ("original", "extended", "adaptive", "sim", "simonline"), the foreground as audio - background,
+    and the mixture / background / foreground spectrograms abs(_stft(mean(x, axis=1)))[0:number_frequencies],
+    all on the device from buffers already resident.
+
+    Output: dict with background, foreground (number_samples, number_channels); audio_spectrogram,
+    background_spectrogram, foreground_spectrogram (number_frequencies, number_times); integers.
+    """
+    return _host.separate_f64(method, audio_signal, sampling_frequency, _tunables(), spectrograms=spectrograms)
+
+
+def spectrogram(audio_signal, sampling_frequency):
+    """Magnitude spectrogram of the channel mean as the reference's examples compute it (README.md:79):
+    abs(_stft(mean(audio_signal, axis=1), hamming, N/2))[0:N/2+1] -> (number_frequencies, number_times)."""
+    audio_signal = np.asarray(audio_signal, dtype=float)
+    if audio_signal.ndim == 1:
+        audio_signal = audio_signal[:, np.newaxis]
+    params, window_function = _host.derive_params(sampling_frequency, _tunables())
+    half = _host.stft_half(np.mean(audio_signal, axis=1)[np.newaxis, :], window_function, params.step_length)[0]
+    return np.abs(half).T
+
+
+def spectrogram_db(audio_spectrogram):
+    """The image `specshow` displays (repet.py:982): 20*log10 of a magnitude spectrogram."""
+    return 20 * np.log10(audio_spectrogram)
+
+
 class SimOnline(_host.SimOnlineStream):
     """Streaming front end of the online REPET-SIM: `SimOnline(sampling_frequency, number_channels)`, then
     `process(block)` per block of samples and `flush()` at the end; the concatenated outputs equal
@@ -187,7 +218,7 @@ def specshow(audio_spectrogram, time_duration, maximum_frequency, xtick_step=1, 
     xtick_labels = np.arange(xtick_step, time_duration, xtick_step).astype(int)
     ytick_locations = np.arange(ytick_step * frequency_resolution, number_frequencies, ytick_step * frequency_resolution)
     ytick_labels = np.arange(ytick_step, maximum_frequency, ytick_step).astype(int)
-    plt.imshow(20 * np.log10(audio_spectrogram), aspect="auto", cmap="jet", origin="lower")
+    plt.imshow(spectrogram_db(audio_spectrogram), aspect="auto", cmap="jet", origin="lower")
     plt.xticks(ticks=xtick_locations, labels=xtick_labels)
     plt.yticks(ticks=ytick_locations, labels=ytick_labels)
     plt.xlabel("Time (s)")

@@ -96,6 +96,11 @@ SIGNATURES = {
     "repet_simonline_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_simonline_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
     "repet_simonline_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
+    "repet_separate_f64": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _pp, _vp, _vp, _vp, _vp, _c_int]),
+    "repet_spectrogram_pitch": (_c_int, [_pp]),
+    "repet_spectrogram_frames": (_c_int, [_pp, _c_i64]),
+    "repet_spectrogram_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp]),
+    "repet_foreground_dev": (_c_int, [_vp, _vp, _vp, _c_i64, _vp]),
     "repet_stft": (_c_int, [_vp, _vp, _c_int, _c_i64, _vp, _vp, _vp]),
     "repet_istft": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_double, _vp]),
     "repet_beatspectrum": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
@@ -465,6 +470,79 @@ def _single_f64(entry, driver, audio_signal, sampling_frequency, tunables, handl
         )
     )
     return background, ints[:capacity]
+
+
+METHODS = {"original": 0, "extended": 1, "adaptive": 2, "sim": 3, "simonline": 4}
+
+
+def separate_f64(method, audio_signal, sampling_frequency, tunables, handle=None, spectrograms=True):
+    """One call for the reference's documented usage (README.md:64-81): background by `method`,
+    foreground = audio - background, and the display spectrograms abs(_stft(mean(x, axis=1)))[0:F] of
+    mixture, background and foreground, all produced on the device from the buffers already there.
+    Returns a dict: background, foreground (number_samples, number_channels) float64;
+    audio_spectrogram, background_spectrogram, foreground_spectrogram (number_frequencies, number_times)
+    float64 (when `spectrograms`); integers = the method's integer output (period(s) or packed lists)."""
+    if method not in METHODS:
+        raise ValueError("method must be one of %s" % sorted(METHODS))
+    number_samples, number_channels = np.shape(audio_signal)
+    handle = handle or get_handle()
+    lib = handle.lib
+    params, _ = derive_params(sampling_frequency, tunables, method)
+    handle.ensure_window(params.window_length)
+    audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
+    background = np.empty((number_samples, number_channels), dtype=np.float64)
+    foreground = np.empty((number_samples, number_channels), dtype=np.float64)
+    number_frames = lib.repet_spectrogram_frames(ctypes.byref(params), number_samples)
+    number = int(tunables["similarity_number"])
+    if method == "original":
+        capacity = 1
+    elif method == "extended":
+        capacity = max(1, lib.repet_extended_segments(ctypes.byref(params), number_samples))
+    elif method == "adaptive":
+        capacity = number_frames
+    elif method == "sim":
+        capacity = number_frames * (number + 1)
+    else:
+        capacity = max(0, lib.repet_simonline_frames(ctypes.byref(params), number_samples)) * (number + 1)
+    ints = np.zeros(max(1, capacity), dtype=np.int32)
+    pitch = lib.repet_spectrogram_pitch(ctypes.byref(params))
+    spec = np.empty((3, number_frames, pitch), dtype=np.float32) if spectrograms else None
+    handle.check(
+        lib.repet_separate_f64(
+            handle.h, METHODS[method], _ptr(audio), number_samples, number_channels, ctypes.byref(params),
+            _ptr(background), _ptr(foreground), _ptr(spec), _ptr(ints), len(ints),
+        )
+    )
+    result = {"background": background, "foreground": foreground, "integers": ints[:capacity]}
+    if spectrograms:
+        number_frequencies = params.window_length // 2 + 1
+        for i, name in enumerate(("audio_spectrogram", "background_spectrogram", "foreground_spectrogram")):
+            result[name] = spec[i, :, :number_frequencies].T.astype(np.float64)
+    return result
+
+
+def spectrogram_batch_device(audio_ptr, spectrogram_ptr, number_clips, number_channels, number_samples,
+                             sampling_frequency, tunables, handle=None):
+    """Display spectrograms |STFT(mean_c x)| of device-resident fp32 planar clips (raw device pointers):
+    spectrogram (clips, frames, pitch) fp32 with pitch = repet_spectrogram_pitch.  Returns (frames, pitch)."""
+    handle = handle or get_handle()
+    params, _ = derive_params(sampling_frequency, tunables)
+    handle.ensure_window(params.window_length)
+    handle.check(
+        handle.lib.repet_spectrogram_batch_dev(
+            handle.h, _vp(audio_ptr), number_clips, number_channels, number_samples, ctypes.byref(params),
+            _vp(spectrogram_ptr),
+        )
+    )
+    return (handle.lib.repet_spectrogram_frames(ctypes.byref(params), number_samples),
+            handle.lib.repet_spectrogram_pitch(ctypes.byref(params)))
+
+
+def foreground_device(audio_ptr, background_ptr, foreground_ptr, number_elements, handle=None):
+    """foreground = audio - background over device-resident fp32 buffers (raw device pointers)."""
+    handle = handle or get_handle()
+    handle.check(handle.lib.repet_foreground_dev(handle.h, _vp(audio_ptr), _vp(background_ptr), number_elements,
+                                                 _vp(foreground_ptr)))
 
 
 def extended_f64(audio_signal, sampling_frequency, tunables, handle=None, return_periods=False):

@@ -330,3 +330,20 @@ def test_period_certification_path(repet):
     for i in range(audio.shape[0]):
         _, det = oracle.original(audio[i].T.astype(np.float64), FS, return_details=True)
         assert int(certified[i]) == det["period"], i
+
+
+def test_adaptive_period_certification_path(repet):
+    """The same for the per-segment periods of the adaptive REPET (segments are windows of the clip's power
+    spectrogram, zero outside the clip): with the certification window widened to 20 % most segments take the
+    float64 re-evaluation, and every frame's period must still equal the oracle's."""
+    audio = _batch(3, 24.0, first=340)
+    _, fast = repet.adaptive_batch(audio, FS)
+    repet._host.set_tuning(cert_rel_ppm=200000)
+    try:
+        _, certified = repet.adaptive_batch(audio, FS)
+    finally:
+        repet._host.set_tuning(cert_rel_ppm=0)
+    assert np.array_equal(fast, certified)
+    for i in range(audio.shape[0]):
+        _, det = oracle.adaptive(audio[i].T.astype(np.float64), FS, return_details=True)
+        assert np.array_equal(certified[i], det["periods"]), i
