@@ -282,6 +282,10 @@ __device__ __forceinline__ double warp_dot64(const double* __restrict__ a, const
 constexpr int TOPK_THREADS = 512;
 constexpr int TOPK_CAP = 2048;       // candidates per column held in shared memory
 constexpr int TOPK_CHUNK = 4096;     // elements of the fast row resident at a time (3 arrays); 88 KB -> 2 CTAs/SM
+constexpr int TOPK_BINS = 512;       // histogram of fast values over [-1, 1) for the top-`number` cut
+__device__ __forceinline__ int topk_bin(float v) {
+    return min(TOPK_BINS - 1, max(0, (int)floorf((v + 1.f) * (TOPK_BINS / 2.f))));
+}
 
 __global__ void __launch_bounds__(TOPK_THREADS)
 k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, float tau, double thr, int d, int number,
@@ -295,6 +299,7 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     float* s_pm = s_e + TOPK_CHUNK;                            // prefix maxima within blocks of d
     float* s_sm = s_pm + TOPK_CHUNK;                           // suffix maxima within blocks of d
     __shared__ int s_count, s_kept;
+    __shared__ float s_cut;
     const int item = blockIdx.y, c = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const float* __restrict__ row = S + ((size_t)item * T + c) * (size_t)T;
@@ -309,17 +314,32 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     // ---- propose: sliding-window maxima by van Herk / Gil-Werman on chunks of the row -----------
     // chunk = nb blocks of d elements: one halo block on each side, nb-2 payload blocks
     const int payload = d > 0 ? (nb - 2) * d : TOPK_CHUNK;
+    const int ext = d > 0 ? nb * d : payload;     // elements staged per chunk (<= TOPK_CHUNK)
+    const int halo = d > 0 ? d : 0;
+    // the next chunk of the row is fetched into registers while the current one is examined
+    constexpr int PER_THREAD = TOPK_CHUNK / TOPK_THREADS;
+    float nxt[PER_THREAD];
+    auto fetch = [&](int g0) {
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; ++u) {
+            const int x = t + u * TOPK_THREADS;
+            const int g = g0 - halo + x;
+            nxt[u] = (x < ext && g >= 0 && g < T) ? __ldg(row + g) : -INFINITY;
+        }
+    };
+    fetch(0);
     for (int g0 = 0; g0 < T; g0 += payload) {
         __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; ++u) {
+            const int x = t + u * TOPK_THREADS;
+            float v = nxt[u];
+            if (v != v) v = INFINITY;  // NaN is never a maximum and blocks its neighbours (quirk Q7)
+            if (x < ext) s_e[x] = v;
+        }
+        if (g0 + payload < T) fetch(g0 + payload);
+        __syncthreads();
         if (d > 0) {
-            const int ext = nb * d;
-            for (int x = t; x < ext; x += blockDim.x) {
-                const int g = g0 - d + x;
-                float v = (g >= 0 && g < T) ? row[g] : -INFINITY;
-                if (v != v) v = INFINITY;  // NaN is never a maximum and blocks its neighbours (quirk Q7)
-                s_e[x] = v;
-            }
-            __syncthreads();
             for (int blk = t; blk < nb; blk += blockDim.x) {
                 float m = -INFINITY;
                 for (int x = blk * d; x < (blk + 1) * d; ++x) {
@@ -331,14 +351,6 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
                     m = fmaxf(m, s_e[x]);
                     s_sm[x] = m;
                 }
-            }
-            __syncthreads();
-        } else {
-            for (int x = t; x < payload; x += blockDim.x) {
-                const int g = g0 + x;
-                float v = g < T ? row[g] : -INFINITY;
-                if (v != v) v = INFINITY;
-                s_e[x] = v;
             }
             __syncthreads();
         }
@@ -370,6 +382,69 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
         count = TOPK_CAP;
     }
     if (t == 0) atomicAdd(overflow + 1, count);  // statistics: candidates proposed
+    // ---- prune: only the `number` best survive the ranking ---------------------------------------
+    // Let c be a value that at least `number` CERTAIN candidates (kept whatever the exact values say)
+    // reach in the fast pass.  A candidate with v~ < c - 2 tau is exactly below all of them, so it can
+    // never be written; it needs no exact value and takes no part in the ranking.  c comes from a
+    // histogram of the certain candidates (bin width 2^-8), conservative by up to one bin.
+    if (count > number) {
+        int* s_hist = reinterpret_cast<int*>(s_pm);  // the chunk buffers are free now
+        for (int b = t; b < TOPK_BINS; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        for (int q = t; q < count; q += blockDim.x)
+            if (!(s_cand[q] & (1 << 30))) atomicAdd(&s_hist[topk_bin(s_vc[q])], 1);
+        __syncthreads();
+        if (warp == 0) {
+            constexpr int PER_LANE = TOPK_BINS / 32;
+            int mine = 0;
+#pragma unroll
+            for (int u = 0; u < PER_LANE; ++u) mine += s_hist[lane * PER_LANE + u];
+            int above = 0;  // certain candidates in the bins of higher lanes
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                const int other = __shfl_sync(0xffffffffu, mine, o);
+                if (o > lane) above += other;
+            }
+            const bool holds = above < number && above + mine >= number;
+            const unsigned who = __ballot_sync(0xffffffffu, holds);
+            if (who == 0) {
+                if (lane == 0) s_cut = -INFINITY;  // fewer than `number` certain candidates: nothing to prune
+            } else if (lane == __ffs(who) - 1) {
+                int cum = above, b = lane * PER_LANE + PER_LANE - 1;
+                for (; b > lane * PER_LANE; --b) {
+                    cum += s_hist[b];
+                    if (cum >= number) break;
+                }
+                s_cut = (float)b * (2.f / TOPK_BINS) - 1.f - two_tau - 1e-6f;  // lower edge of the bin, minus 2 tau (and binning rounding)
+            }
+        }
+        __syncthreads();
+        const float cut = s_cut;
+        if (cut > -INFINITY) {
+            // compact the survivors in place (one warp, chunks of 32 in order: writes never pass reads)
+            if (warp == 0) {
+                int kept = 0;
+                for (int q0 = 0; q0 < count; q0 += 32) {
+                    const int q = q0 + lane;
+                    const int code = q < count ? s_cand[q] : 0;
+                    const float v = q < count ? s_vc[q] : 0.f;
+                    const bool keep = q < count && v >= cut;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    __syncwarp();
+                    if (keep) {
+                        const int pos = kept + __popc(m & ((1u << lane) - 1));
+                        s_cand[pos] = code;
+                        s_vc[pos] = v;
+                    }
+                    kept += __popc(m);
+                    __syncwarp();
+                }
+                if (lane == 0) s_count = kept;
+            }
+            __syncthreads();
+            count = s_count;
+        }
+    }
     // ---- which candidates need their exact value? ---------------------------------------------
     // the uncertain ones (local-maximum test within 2 tau) and every pair whose fast values are within
     // 2 tau of each other (their ORDER is not decided by the fast pass); bit 29 marks them
