@@ -66,7 +66,7 @@ void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64,
 // value -- enough to flip near-tied candidates on a long track -- so the operand of the similarity
 // (An64, and the TF32 operands rounded from it) is rebuilt here with a float64 transform; the fp32
 // spectra of k_stft are only used for the mask and the resynthesis (tolerance 1e-4).
-// One CTA per frame: both channels packed into one complex transform (z = w (xL + i xR)), radix-2
+// One CTA per frame: both channels packed into one complex transform (z = w (xL + i xR)), radix-4
 // Stockham autosort between two shared-memory buffers, Hermitian split, magnitudes by hypot (as
 // np.abs), channel mean, float64 norm, and the three operand formats written in one pass.
 // An all-zero frame gives 0/0 = NaN as in the reference (quirk Q18).
@@ -106,14 +106,39 @@ k_frames64(const float* __restrict__ audio, const double* __restrict__ audio64, 
     __syncthreads();
     double2* src = bufA;
     double2* dst = bufB;
-    for (int ns = 1; ns < WIN_N; ns <<= 1) {
-        const int tw_step = WIN_N / (2 * ns);
+    // W_N^i for any i < N from the half table: W_N^(i + N/2) = -W_N^i
+    auto twiddle = [&](int i) {
+        const double2 w = tw64[i & (WIN_N / 2 - 1)];
+        return (i & (WIN_N / 2)) ? make_double2(-w.x, -w.y) : w;
+    };
+    auto cmul64 = [](double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); };
+    int ns = 1;
+    for (; ns * 4 <= WIN_N; ns <<= 2) {  // radix-4 Stockham stages
+        const int tw_step = WIN_N / (4 * ns);
+        for (int q = t; q < WIN_N / 4; q += F64_THREADS) {
+            const int k = q & (ns - 1);
+            const double2 a0 = src[q];
+            const double2 a1 = cmul64(src[q + WIN_N / 4], twiddle(k * tw_step));
+            const double2 a2 = cmul64(src[q + WIN_N / 2], twiddle(2 * k * tw_step));
+            const double2 a3 = cmul64(src[q + 3 * (WIN_N / 4)], twiddle(3 * k * tw_step));
+            const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
+            const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
+            const int o = ((q - k) << 2) + k;
+            dst[o] = make_double2(s02.x + s13.x, s02.y + s13.y);
+            dst[o + ns] = make_double2(d02.x + d13.y, d02.y - d13.x);      // a0 - i a1 - a2 + i a3
+            dst[o + 2 * ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
+            dst[o + 3 * ns] = make_double2(d02.x - d13.y, d02.y + d13.x);  // a0 + i a1 - a2 - i a3
+        }
+        __syncthreads();
+        double2* tmp = src;
+        src = dst;
+        dst = tmp;
+    }
+    if (ns < WIN_N) {  // one radix-2 stage left when log2 N is odd
         for (int q = t; q < WIN_N / 2; q += F64_THREADS) {
             const int k = q & (ns - 1);
-            const double2 w = tw64[k * tw_step];
             const double2 a = src[q];
-            const double2 b0 = src[q + WIN_N / 2];
-            const double2 b = make_double2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
+            const double2 b = cmul64(src[q + WIN_N / 2], twiddle(k * (WIN_N / (2 * ns))));
             const int o = ((q - k) << 1) + k;
             dst[o] = make_double2(a.x + b.x, a.y + b.y);
             dst[o + ns] = make_double2(a.x - b.x, a.y - b.y);

@@ -12,6 +12,8 @@
 //   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (TMEM -> registers), transpose through a padded
 //               smem tile so that global stores are 128-byte coalesced rows, predicated on the
 //               ragged edges; overlaps the next tile's MMAs through the second accumulator
+// With square tiles (split configuration) only the upper triangle of tiles is computed; the epilogue writes
+// every off-diagonal tile and its mirror image.
 // The result only PROPOSES similar-frame candidates: k_topk certifies every decision with exact
 // float64 dot products, with tau covering the TF32 rounding (|S~ - S| <= 2 * 2^-11 + accumulation).
 #include "repet_kernels.cuh"
@@ -116,6 +118,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Tile schedule.  S = A A^T is symmetric: with square tiles (the split configuration) only the tiles on and
+// above the diagonal are computed and the epilogue writes each off-diagonal tile twice (once mirrored), which
+// halves the MMAs.  Upper-triangle tiles are numbered row by row: row mi starts at mi*nt - mi*(mi-1)/2.
+template <bool TRI>
+__device__ __forceinline__ void decode_tile(int tile, int mt, int nt, int& item, int& mi, int& ni) {
+    if (!TRI) {
+        item = tile / (mt * nt);
+        const int rem = tile - item * (mt * nt);
+        mi = rem / nt;
+        ni = rem - mi * nt;
+        return;
+    }
+    const int per_item = nt * (nt + 1) / 2;
+    item = tile / per_item;
+    const int u = tile - item * per_item;
+    const float b = (float)(2 * nt + 1);
+    int r = (int)((b - sqrtf(fmaxf(b * b - 8.f * (float)u, 0.f))) * 0.5f);
+    r = max(0, min(nt - 1, r));
+    while (r > 0 && r * nt - r * (r - 1) / 2 > u) --r;
+    while (r + 1 < nt && (r + 1) * nt - (r + 1) * r / 2 <= u) ++r;
+    mi = r;
+    ni = r + (u - (r * nt - r * (r - 1) / 2));
+}
+
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -138,8 +164,9 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool TRI = BM == BN;
     const int mt = (T + BM - 1) / BM, nt = (T + BN - 1) / BN;
-    const int tiles_total = n_items * mt * nt;
+    const int tiles_total = n_items * (TRI ? nt * (nt + 1) / 2 : mt * nt);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -168,8 +195,9 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-                const int item = tile / (mt * nt), rem = tile - item * (mt * nt);
-                const int m0 = (rem / nt) * BM, n0 = (rem % nt) * BN;
+                int item, mi, ni;
+                decode_tile<TRI>(tile, mt, nt, item, mi, ni);
+                const int m0 = mi * BM, n0 = ni * BN;
                 for (int kb = 0; kb < KBLOCKS; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -222,8 +250,10 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         float* stage = epi + quarter * 32 * EPI_PITCH;
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++tile_iter) {
-            const int item = tile / (mt * nt), rem = tile - item * (mt * nt);
-            const int m0 = (rem / nt) * BM, n0 = (rem % nt) * BN;
+            int item, mi, ni;
+            decode_tile<TRI>(tile, mt, nt, item, mi, ni);
+            const int m0 = mi * BM, n0 = ni * BN;
+            const bool mirror = TRI && ni != mi;
             const uint32_t acc = tile_iter & 1;
             mbar_wait(&acc_full[acc], (tile_iter >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -236,6 +266,14 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 // thread = row, v = 32 consecutive columns  ->  smem [row][col], read back [col] per row
 #pragma unroll
                 for (int c = 0; c < 32; ++c) stage[lane * EPI_PITCH + c] = __uint_as_float(v[c]);
+                if (mirror && row_base + lane < T) {
+                    // S[col][row] = S[row][col]: for a fixed column the 32 lanes hold 32 consecutive rows, so the
+                    // mirrored tile goes out as 128-byte rows straight from the registers
+                    float* __restrict__ dst = Sitem + (size_t)(n0 + chunk * 32) * T + row_base + lane;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (n0 + chunk * 32 + c < T) dst[(size_t)c * T] = __uint_as_float(v[c]);
+                }
                 __syncwarp();
                 const int col = n0 + chunk * 32 + lane;
                 if (col < T) {
@@ -301,7 +339,7 @@ int launch_gemm(cudaStream_t st, const float* hi, const float* lo, int n_items, 
         configured = true;
     }
     const int mt = (T + BM - 1) / BM, nt = (T + BN - 1) / BN;
-    const int tiles_total = n_items * mt * nt;
+    const int tiles_total = n_items * (BM == BN ? nt * (nt + 1) / 2 : mt * nt);
     const int grid = std::max(1, std::min(tiles_total, sm_count));
     k_simgemm<BN, SPLIT3><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(map_a, map_b, map_a_lo, map_b_lo, T, n_items, S);
     return 0;

@@ -90,7 +90,11 @@ def main():
             T = int(np.ceil(S / 1024)) + 1
             gemm_ms = prof.get("k_simgemm", (0, 0))[0] / args.steps
             if gemm_ms:
-                line["gemm_useful_tflops"] = 2.0 * T * T * 1025 / (gemm_ms / 1e3) / 1e12
+                # only the triangle of S = A A^T is formed (square tiles), so the useful work is
+                # T (T+1) F flop; the full-product figure says what a caller of the whole matrix gets per second
+                line["gemm_useful_tflops"] = float(T) * (T + 1) * 1025 / (gemm_ms / 1e3) / 1e12
+                line["gemm_full_product_equivalent_tflops"] = 2.0 * T * T * 1025 / (gemm_ms / 1e3) / 1e12
+                line["gemm_tf32_mma_tflops_issued"] = 3 * line["gemm_useful_tflops"] * 1056 / 1025
         print(json.dumps(line), flush=True)
         del audio, out
         torch.cuda.empty_cache()
