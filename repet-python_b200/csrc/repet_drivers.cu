@@ -115,7 +115,7 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
                 launch_beat(st, P, g_items, s.T, 0, s.T, 0, 1, tables(h), psd, s.n_parts, s.f_per_part);
         }
         {
-            Timed timed(h, REPET_K_PERIODS);
+            Timed timed(h, REPET_K_PERIODS, 3);  // k_periods, k_period_certify, k_period_finalize
             launch_periods(st, psd, psd_im, g_items, total_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr,
                            0, periods_dev + first, nullptr, cert);
             launch_period_certify(st, P, g_items, s.T, 0, s.T, 0, 1, cert, cert_val, periods_dev + first);
@@ -355,7 +355,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
                 return fail(h, REPET_E_UNSUPPORTED, "track too long for the in-shared-memory similarity row");
         }
         {
-            Timed timed(h, REPET_K_MODEL);
+            Timed timed(h, REPET_K_MODEL, Vsq ? 3 : 1);  // k_sqmag, k_simmodel, k_simmodel_large
             if (Vsq) launch_sqmag(st, X, (long long)g * T * nch, Vsq);
             if (launch_simmodel(st, X, Vsq, g, T, nch, idx, cnt, plan.number, geom.first_frame, model))
                 return fail(h, REPET_E_UNSUPPORTED, "similarity_number too large for the shared-memory median");
@@ -460,14 +460,14 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
                         plan.beat_parts, plan.beat_f_per_part);
         }
         {
-            Timed timed(h, REPET_K_PERIODS);
+            Timed timed(h, REPET_K_PERIODS, 3);
             launch_periods(st, psd, nullptr, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
                            plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr, cert);
             launch_period_certify(st, P, g * plan.n_beat_seg, T, -plan.left_pad, plan.seg_frames, plan.step_frames,
                                   plan.n_beat_seg, cert, cert_val, seg_period);
         }
         {
-            Timed timed(h, REPET_K_MODEL);
+            Timed timed(h, REPET_K_MODEL, 2);
             launch_expand_periods(st, seg_period, g, plan.n_beat_seg, T, plan.step_frames, plan.p.period_lo, frame_period);
             launch_adaptive_model(st, X, g, T, nch, frame_period, plan.p.filter_order, model);
         }

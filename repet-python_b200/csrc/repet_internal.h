@@ -107,11 +107,12 @@ struct Bump {
     }
 };
 
-// Brackets one launch with an event pair when profiling is on; always counts the launch.
+// Brackets the launches of one pipeline step with an event pair when profiling is on; always counts the
+// kernels launched inside (`kernels`, default one).
 struct Timed {
     repet_handle* h;
-    Timed(repet_handle* handle, int id) : h(handle) {
-        h->launches += 1;
+    Timed(repet_handle* handle, int id, int kernels = 1) : h(handle) {
+        h->launches += kernels;
         if (!h->profiling) return;
         if (h->prof_used + 2 > h->prof_events.size()) {
             for (int i = 0; i < 2; ++i) {
