@@ -566,17 +566,28 @@ int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items
 // k_online_select  --  the per-frame selection of the online REPET-SIM     repet.py:834-866
 // Frame j (>= B-1) is compared with the B frames in its ring buffer, visited in SLOT order:
 // slot b holds frame j-(j0-b) for b <= j0 and j-(j0-b)-B for b > j0, j0 = j mod B (quirk Q6).
-// Similarities are exact float64 dots of the float64-normalised frames, so the local-maximum
-// rule and the ranking need no certification.  Writes FRAME indices.
+// Similarities are exact float64 dots of the float64-normalised frames (float64 tensor-core MMAs,
+// mma.sync m8n8k4), so the local-maximum rule and the ranking need no certification.  Writes FRAME indices.
 // ------------------------------------------------------------------------------------------
-constexpr int ONLINE_FB = 8;  // target frames per CTA
+constexpr int ONLINE_FB = 16;                  // target frames per CTA: two 8-row A blocks of the float64 MMA
+constexpr int TGT_PITCH = APITCH64 + 10;       // doubles per target row in shared memory; pitch % 16 == 2 keeps the
+                                               // 16-byte A-fragment loads of a quarter warp on disjoint banks
+static_assert(TGT_PITCH % 16 == 2, "target row pitch");
+
+// D (8x8) += A (8x4, row major) * B (4x8, column major), float64 tensor-core MMA.  Lane l holds
+// A[l/4][l%4], B[l%4][l/4] and D[l/4][2*(l%4) + {0, 1}].
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
 
 __global__ void __launch_bounds__(256)
 k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, double thr, int d, int number,
                 int* __restrict__ idx_out, int* __restrict__ cnt_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* s_tgt = reinterpret_cast<double*>(smem);          // [ONLINE_FB][APITCH64]  target frames
-    double* s_sim = s_tgt + ONLINE_FB * APITCH64;             // [ONLINE_FB][B]         similarity by ring slot
+    double* s_tgt = reinterpret_cast<double*>(smem);          // [ONLINE_FB][TGT_PITCH]  target frames
+    double* s_sim = s_tgt + ONLINE_FB * TGT_PITCH;            // [ONLINE_FB][B]          similarity by ring slot
     unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_sim + ONLINE_FB * B);  // [ONLINE_FB][B]
     __shared__ int s_kept[ONLINE_FB];
     const int item = blockIdx.y;
@@ -589,64 +600,140 @@ k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, d
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const double* __restrict__ A = An64 + (size_t)item * T * APITCH64;
     if (t < ONLINE_FB) s_kept[t] = 0;
-    for (int k = t; k < nf * APITCH64; k += blockDim.x) s_tgt[k] = A[(size_t)j_first * APITCH64 + k];
+    for (int e = t; e < ONLINE_FB * APITCH64; e += blockDim.x) {
+        const int f = e / APITCH64, k = e - f * APITCH64;
+        s_tgt[f * TGT_PITCH + k] = f < nf ? A[(size_t)(j_first + f) * APITCH64 + k] : 0.0;
+    }
     // slots whose frame lies before the window (a stream window with partial history) can never be maxima
     for (int e = t; e < nf * B; e += blockDim.x) s_sim[e] = -INFINITY;
     __syncthreads();
-    // Frame u sits in ring slot u mod B.  Every buffer frame of the block's targets is read ONCE and
-    // dotted (exact float64) against all the targets it belongs to: u in [j-B+1, j].
+    // Frame u sits in ring slot u mod B.  The similarities of the block's 16 targets with every buffer frame
+    // u in [j_first - B + 1, j_first + nf - 1] are exact float64 dot products on the float64 tensor cores:
+    // a warp takes 8 buffer frames at a time (B operand, streamed once from L2 in 128-byte row pieces) against
+    // both 8-target blocks (A operand, shared memory).  The bins are visited in a lane-permuted order (lane
+    // quad member q owns bins 16 c + 4 q .. + 3 of chunk c, one per MMA) so that every lane loads 32 contiguous
+    // bytes; a sum does not care about the order of its terms.
     const int u_lo = max(0, j_first - (B - 1)), u_hi = j_first + nf - 1;
-    for (int u = u_lo + warp; u <= u_hi; u += nwarp) {
-        double a[DOTN];
-        const double* __restrict__ row = A + (size_t)u * APITCH64;
+    const int n_blocks = (u_hi - u_lo + 8) >> 3;
+    const int fr = lane >> 2, q = lane & 3;
+    for (int nb = warp; nb < n_blocks; nb += nwarp) {
+        const int u0 = u_lo + 8 * nb;
+        const double* __restrict__ brow = A + (size_t)min(u0 + fr, u_hi) * APITCH64 + 4 * q;
+        const double* __restrict__ arow0 = s_tgt + fr * TGT_PITCH + 4 * q;
+        const double* __restrict__ arow1 = arow0 + 8 * TGT_PITCH;
+        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+        // groups of 4 chunks (64 bins): the B fragments of the next group are in flight (8 x 16-byte loads per
+        // lane) while the 32 MMAs of the current one run -- without this every chunk waits out an L2 round trip
+        constexpr int GROUP = 4, N_GROUPS = (NBIN - 1) / (16 * GROUP);
+        static_assert((NBIN - 1) % (16 * GROUP) == 0, "bins - 1 must be a multiple of 64");
+        double2 bn[2 * GROUP];
 #pragma unroll
-        for (int i = 0; i < DOTN; ++i) {
-            const int k = lane + 32 * i;
-            a[i] = k < NBIN ? row[k] : 0.0;
+        for (int i = 0; i < GROUP; ++i) {
+            bn[2 * i] = __ldg(reinterpret_cast<const double2*>(brow + 16 * i));
+            bn[2 * i + 1] = __ldg(reinterpret_cast<const double2*>(brow + 16 * i + 2));
         }
-        const int slot = (u + frame_base) % B;
-        for (int f = 0; f < nf; ++f) {
-            const int j = j_first + f;
-            if (u > j || u < j - (B - 1)) continue;  // warp-uniform
-            const double* __restrict__ tg = s_tgt + f * APITCH64;
-            double s = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < N_GROUPS; ++g) {
+            double2 bc[2 * GROUP];
 #pragma unroll
-            for (int i = 0; i < DOTN; ++i) {
-                const int k = lane + 32 * i;
-                if (k < NBIN) s = fma(a[i], tg[k], s);
+            for (int i = 0; i < 2 * GROUP; ++i) bc[i] = bn[i];
+            if (g + 1 < N_GROUPS) {
+                const double* __restrict__ nxt = brow + 16 * GROUP * (g + 1);
+#pragma unroll
+                for (int i = 0; i < GROUP; ++i) {
+                    bn[2 * i] = __ldg(reinterpret_cast<const double2*>(nxt + 16 * i));
+                    bn[2 * i + 1] = __ldg(reinterpret_cast<const double2*>(nxt + 16 * i + 2));
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_sim[f * B + slot] = s;
+            for (int i = 0; i < GROUP; ++i) {
+                const int k0 = 16 * (GROUP * g + i);
+                const double2 x01 = *reinterpret_cast<const double2*>(arow0 + k0);
+                const double2 x23 = *reinterpret_cast<const double2*>(arow0 + k0 + 2);
+                const double2 y01 = *reinterpret_cast<const double2*>(arow1 + k0);
+                const double2 y23 = *reinterpret_cast<const double2*>(arow1 + k0 + 2);
+                dmma884(c0, x01.x, bc[2 * i].x);
+                dmma884(c1, y01.x, bc[2 * i].x);
+                dmma884(c0, x01.y, bc[2 * i].y);
+                dmma884(c1, y01.y, bc[2 * i].y);
+                dmma884(c0, x23.x, bc[2 * i + 1].x);
+                dmma884(c1, y23.x, bc[2 * i + 1].x);
+                dmma884(c0, x23.y, bc[2 * i + 1].y);
+                dmma884(c1, y23.y, bc[2 * i + 1].y);
+            }
+        }
+        // lane holds the sums of targets fr and fr + 8 with frames u0 + 2 q and u0 + 2 q + 1; the last bin
+        // (NBIN - 1, the Nyquist row) is the one left over by the chunks of 16
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int u = u0 + 2 * q + e;
+            if (u > u_hi) continue;
+            const double last = __ldg(A + (size_t)u * APITCH64 + (NBIN - 1));
+            const int slot = (u + frame_base) % B;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int f = fr + 8 * half;
+                const int j = j_first + f;
+                if (f >= nf || u > j || u < j - (B - 1)) continue;
+                const double sum = half ? c1[e] : c0[e];
+                s_sim[f * B + slot] = fma(s_tgt[f * TGT_PITCH + (NBIN - 1)], last, sum);
+            }
         }
     }
     __syncthreads();
-    // strict local maxima in slot order, windows clipped at slots 0 and B-1 (not circular), quirk Q6
-    for (int e = t; e < nf * B; e += blockDim.x) {
-        const int f = e / B, b = e - f * B;
-        const double* __restrict__ sim = s_sim + f * B;
-        const double v = sim[b];
-        bool keep = v >= thr;
-        const int lo = max(b - d, 0), hi = min(b + d, B - 1);
-        for (int x = lo; x <= hi && keep; ++x)
-            if (x != b && !(v > sim[x])) keep = false;
-        s_keep[e] = keep ? 1 : 0;
+    // strict local maxima in slot order, windows clipped at slots 0 and B-1 (not circular), quirk Q6.
+    // Both passes are warp-cooperative: a warp looks at 32 consecutive entries, compacts the few that matter
+    // with a ballot (entries above both direct neighbours; then the kept ones) and spreads each one's window /
+    // ranking loop over its lanes -- per-thread loops left 31 lanes waiting for the one that held a maximum.
+    const int n_entries = nf * B;
+    for (int e0 = warp * 32; e0 < n_entries; e0 += nwarp * 32) {
+        const int e = e0 + lane;
+        bool cand = false;
+        if (e < n_entries) {
+            const int f = e / B, b = e - f * B;
+            const double* __restrict__ sim = s_sim + f * B;
+            const double v = sim[b];
+            cand = v >= thr;
+            if (d > 0 && cand) cand = (b == 0 || v > sim[b - 1]) && (b == B - 1 || v > sim[b + 1]);
+            s_keep[e] = (d == 0 && cand) ? 1 : 0;
+        }
+        unsigned todo = d > 0 ? __ballot_sync(0xffffffffu, cand) : 0u;
+        while (todo) {
+            const int ec = e0 + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int f = ec / B, b = ec - f * B;
+            const double* __restrict__ sim = s_sim + f * B;
+            const double v = sim[b];
+            const int lo = max(b - d, 0), hi = min(b + d, B - 1);
+            bool bad = false;
+            for (int x = lo + lane; x <= hi; x += 32) bad |= (x != b && !(v > sim[x]));
+            if (!__any_sync(0xffffffffu, bad) && lane == 0) s_keep[ec] = 1;
+        }
     }
     __syncthreads();
-    for (int e = t; e < nf * B; e += blockDim.x) {
-        if (!s_keep[e]) continue;
-        const int f = e / B, b = e - f * B;
-        const double* __restrict__ sim = s_sim + f * B;
-        const unsigned char* __restrict__ keepf = s_keep + f * B;
-        const double v = sim[b];
-        int rank = 0;
-        for (int x = 0; x < B; ++x)
-            if (x != b && keepf[x]) rank += (sim[x] > v) || (sim[x] == v && x > b);
-        atomicAdd(&s_kept[f], 1);
-        if (rank < number) {
-            const int j = j_first + f, j0 = (j + frame_base) % B;
-            const int frame = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
-            idx_out[((size_t)item * T + j) * (size_t)number + rank] = frame;
+    for (int e0 = warp * 32; e0 < n_entries; e0 += nwarp * 32) {
+        const int e = e0 + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, e < n_entries && s_keep[e]);
+        while (todo) {
+            const int ek = e0 + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int f = ek / B, b = ek - f * B;
+            const double* __restrict__ sim = s_sim + f * B;
+            const unsigned char* __restrict__ keepf = s_keep + f * B;
+            const double v = sim[b];
+            int rank = 0;
+            for (int x = lane; x < B; x += 32)
+                if (x != b && keepf[x]) rank += (sim[x] > v) || (sim[x] == v && x > b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+            if (lane == 0) {
+                atomicAdd(&s_kept[f], 1);
+                if (rank < number) {
+                    const int j = j_first + f, j0 = (j + frame_base) % B;
+                    const int frame = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
+                    idx_out[((size_t)item * T + j) * (size_t)number + rank] = frame;
+                }
+            }
         }
     }
     __syncthreads();
@@ -657,7 +744,7 @@ void launch_online_select(cudaStream_t st, const double* An64, int n_items, int 
                           int d, int number, int* idx_out, int* cnt_out) {
     const int row_first = std::max(0, B - 1 - frame_base);
     if (T <= row_first) return;
-    const size_t smem = (size_t)ONLINE_FB * APITCH64 * 8 + (size_t)ONLINE_FB * B * 9 + 16;
+    const size_t smem = (size_t)ONLINE_FB * TGT_PITCH * 8 + (size_t)ONLINE_FB * B * 9 + 16;
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
         cudaFuncSetAttribute(k_online_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
