@@ -582,7 +582,7 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, double thr, int d, int number,
                 int* __restrict__ idx_out, int* __restrict__ cnt_out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -600,10 +600,9 @@ k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, d
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const double* __restrict__ A = An64 + (size_t)item * T * APITCH64;
     if (t < ONLINE_FB) s_kept[t] = 0;
-    for (int e = t; e < ONLINE_FB * APITCH64; e += blockDim.x) {
-        const int f = e / APITCH64, k = e - f * APITCH64;
-        s_tgt[f * TGT_PITCH + k] = f < nf ? A[(size_t)(j_first + f) * APITCH64 + k] : 0.0;
-    }
+    for (int f = 0; f < ONLINE_FB; ++f)
+        for (int k = t; k < APITCH64; k += blockDim.x)
+            s_tgt[f * TGT_PITCH + k] = f < nf ? __ldg(A + (size_t)(j_first + f) * APITCH64 + k) : 0.0;
     // slots whose frame lies before the window (a stream window with partial history) can never be maxima
     for (int e = t; e < nf * B; e += blockDim.x) s_sim[e] = -INFINITY;
     __syncthreads();
@@ -685,41 +684,42 @@ k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, d
     // Both passes are warp-cooperative: a warp looks at 32 consecutive entries, compacts the few that matter
     // with a ballot (entries above both direct neighbours; then the kept ones) and spreads each one's window /
     // ranking loop over its lanes -- per-thread loops left 31 lanes waiting for the one that held a maximum.
-    const int n_entries = nf * B;
-    for (int e0 = warp * 32; e0 < n_entries; e0 += nwarp * 32) {
-        const int e = e0 + lane;
+    const int chunks = (B + 31) >> 5;  // 32-slot pieces per target
+    for (int w = warp; w < nf * chunks; w += nwarp) {
+        const int f = w / chunks, b0 = (w - f * chunks) << 5;
+        const double* __restrict__ sim = s_sim + f * B;
+        unsigned char* __restrict__ keepf = s_keep + f * B;
+        const int b = b0 + lane;
         bool cand = false;
-        if (e < n_entries) {
-            const int f = e / B, b = e - f * B;
-            const double* __restrict__ sim = s_sim + f * B;
+        if (b < B) {
             const double v = sim[b];
             cand = v >= thr;
-            if (d > 0 && cand) cand = (b == 0 || v > sim[b - 1]) && (b == B - 1 || v > sim[b + 1]);
-            s_keep[e] = (d == 0 && cand) ? 1 : 0;
+            // cheap pre-filter on the four nearest slots of each side before the full window
+            const int near = min(d, 4);
+            for (int o = 1; o <= near && cand; ++o)
+                cand = (b - o < 0 || v > sim[b - o]) && (b + o > B - 1 || v > sim[b + o]);
+            keepf[b] = (d <= 4 && cand) ? 1 : 0;
         }
-        unsigned todo = d > 0 ? __ballot_sync(0xffffffffu, cand) : 0u;
+        unsigned todo = d > 4 ? __ballot_sync(0xffffffffu, cand) : 0u;
         while (todo) {
-            const int ec = e0 + __ffs(todo) - 1;
+            const int bc = b0 + __ffs(todo) - 1;
             todo &= todo - 1;
-            const int f = ec / B, b = ec - f * B;
-            const double* __restrict__ sim = s_sim + f * B;
-            const double v = sim[b];
-            const int lo = max(b - d, 0), hi = min(b + d, B - 1);
+            const double v = sim[bc];
+            const int lo = max(bc - d, 0), hi = min(bc + d, B - 1);
             bool bad = false;
-            for (int x = lo + lane; x <= hi; x += 32) bad |= (x != b && !(v > sim[x]));
-            if (!__any_sync(0xffffffffu, bad) && lane == 0) s_keep[ec] = 1;
+            for (int x = lo + lane; x <= hi; x += 32) bad |= (x != bc && !(v > sim[x]));
+            if (!__any_sync(0xffffffffu, bad) && lane == 0) keepf[bc] = 1;
         }
     }
     __syncthreads();
-    for (int e0 = warp * 32; e0 < n_entries; e0 += nwarp * 32) {
-        const int e = e0 + lane;
-        unsigned todo = __ballot_sync(0xffffffffu, e < n_entries && s_keep[e]);
+    for (int w = warp; w < nf * chunks; w += nwarp) {
+        const int f = w / chunks, b0 = (w - f * chunks) << 5;
+        const double* __restrict__ sim = s_sim + f * B;
+        const unsigned char* __restrict__ keepf = s_keep + f * B;
+        unsigned todo = __ballot_sync(0xffffffffu, b0 + lane < B && keepf[b0 + lane]);
         while (todo) {
-            const int ek = e0 + __ffs(todo) - 1;
+            const int b = b0 + __ffs(todo) - 1;
             todo &= todo - 1;
-            const int f = ek / B, b = ek - f * B;
-            const double* __restrict__ sim = s_sim + f * B;
-            const unsigned char* __restrict__ keepf = s_keep + f * B;
             const double v = sim[b];
             int rank = 0;
             for (int x = lane; x < B; x += 32)
@@ -752,7 +752,7 @@ void launch_online_select(cudaStream_t st, const double* An64, int n_items, int 
     }
     const int n_targets = T - row_first;
     dim3 grid((n_targets + ONLINE_FB - 1) / ONLINE_FB, n_items);
-    k_online_select<<<grid, 256, smem, st>>>(An64, T, B, frame_base, thr, d, number, idx_out, cnt_out);
+    k_online_select<<<grid, 512, smem, st>>>(An64, T, B, frame_base, thr, d, number, idx_out, cnt_out);
 }
 
 // ------------------------------------------------------------------------------------------
