@@ -847,7 +847,22 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                  : "memory");
 }
 
+// mask = min(model, |X|) / |X| (repet.py:1441-1452 with eps = machine epsilon): model * rsqrt(|X|^2) capped at 1.
+// |X| = 0 gives 0 * inf = NaN, which fminf drops in favour of 1 -- the reference's (0 + eps) / (0 + eps) (quirk Q10).
 __device__ __forceinline__ float soft_mask(float model, float v2) { return fminf(model * fast_rsqrt(v2), 1.0f); }
+// The same, but a NaN MODEL stays NaN, as np.minimum keeps it (a REPET-SIM frame whose similar-frame list is
+// empty has np.median([]) = NaN as its model, and the reference's output is NaN over that frame).  Used for the
+// DC bin only: one NaN bin makes the whole inverse transform of the frame NaN, so the other bins can keep the
+// cheaper form.  |X|^2 + FLT_MIN keeps the silent-frame case finite (the masked value is mask * 0 = 0 anyway).
+__device__ __forceinline__ float soft_mask_keep_nan(float model, float v2) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(model * fast_rsqrt(v2 + 1.17549435e-38f)), "f"(1.0f));
+    return r;
+}
+// helper-level mask (returns the mask itself): exact in both special cases
+__device__ __forceinline__ float soft_mask_exact(float model, float v2) {
+    return model != model ? model : soft_mask(model, v2);
+}
 
 // ------------------------------------------------------------------------------------------
 // k_mask_istft  --  rest of _mask + high-pass + mirror + apply + _istft
@@ -962,10 +977,10 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
                     // bin 0 packs DC (mask kept, quirk Q11) and Nyquist, both purely real
                     float m_dc_l = 1.f, m_ny_l = 1.f, m_dc_r = 1.f, m_ny_r = 1.f;
                     if (MASKED) {
-                        m_dc_l = soft_mask(ml[0][0], xl.x * xl.x);
+                        m_dc_l = soft_mask_keep_nan(ml[0][0], xl.x * xl.x);
                         m_ny_l = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&ml_row[XPITCH]), xl.y * xl.y);
                         if (NCH == 2) {
-                            m_dc_r = soft_mask(mr[0][0], xr.x * xr.x);
+                            m_dc_r = soft_mask_keep_nan(mr[0][0], xr.x * xr.x);
                             m_ny_r = (XPITCH <= cutoff) ? 1.f : soft_mask(__ldg(&mr_row[XPITCH]), xr.y * xr.y);
                         }
                     }
@@ -1076,7 +1091,7 @@ k_mask_only(const float2* __restrict__ X, int T, int nch, const int* __restrict_
     const int p = period ? period[item] : pmax;
     const float2* __restrict__ row = X + ((size_t)item * T + j) * (size_t)(nch * XPITCH) + (size_t)c * XPITCH;
     const float m = model[(((size_t)item * nch + c) * pmax + (j % p)) * PPITCH + k];
-    mask_out[(((size_t)item * nch + c) * T + j) * PPITCH + k] = soft_mask(m, row_mag2(row, k));
+    mask_out[(((size_t)item * nch + c) * T + j) * PPITCH + k] = soft_mask_exact(m, row_mag2(row, k));
 }
 
 void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* period, int pmax,
