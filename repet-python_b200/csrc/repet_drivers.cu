@@ -355,7 +355,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
                 return fail(h, REPET_E_UNSUPPORTED, "track too long for the in-shared-memory similarity row");
         }
         {
-            Timed timed(h, REPET_K_MODEL, Vsq ? 3 : 1);  // k_sqmag, k_simmodel, k_simmodel_large
+            Timed timed(h, REPET_K_MODEL, Vsq ? 4 : 2);  // [k_sqmag,] k_simmodel, [k_simmodel_large,] k_simmodel_nyquist
             if (Vsq) launch_sqmag(st, X, (long long)g * T * nch, Vsq);
             if (launch_simmodel(st, X, Vsq, g, T, nch, idx, cnt, plan.number, geom.first_frame, model))
                 return fail(h, REPET_E_UNSUPPORTED, "similarity_number too large for the shared-memory median");

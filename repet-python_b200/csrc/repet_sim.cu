@@ -785,17 +785,7 @@ __device__ __forceinline__ void simmodel_small(const float2* __restrict__ chan, 
 #pragma unroll 1
     for (int k = 2 * t; k < XPITCH; k += 256)
         *reinterpret_cast<float2*>(out + k) = gather_median_pair<N>(chan, row, list, k, k == 0);
-    if (t == 0) {
-        // Nyquist rides in bin 0's imaginary slot
-        float v[N];
-#pragma unroll
-        for (int s = 0; s < N; ++s) {
-            const float y = __ldg(&chan[(size_t)list[s] * row]).y;
-            v[s] = __fmul_rn(y, y);
-        }
-        median_select<N>(v);
-        out[XPITCH] = (N & 1) ? fast_sqrt(v[(N - 1) / 2]) : 0.5f * (fast_sqrt(v[(N - 1) / 2]) + fast_sqrt(v[N / 2]));
-    }
+    // the Nyquist bin (bin 0's imaginary slot) of every frame is done by k_simmodel_nyquist
 }
 
 // median of column `col` of a [n][pitch] shared-memory tile of squared magnitudes: in-place Hoare
@@ -881,7 +871,6 @@ __device__ __forceinline__ void simmodel_large(const float* __restrict__ vchan, 
                                                int n, float* __restrict__ out, int t) {
 #pragma unroll 1
     for (int k = t; k < XPITCH; k += 128) out[k] = gather_median_large<NS>(vchan, vrow, list, n, k);
-    if (t == 0) out[XPITCH] = gather_median_large<NS>(vchan, vrow, list, n, XPITCH);
 }
 
 // k_simmodel_large: lists of 33..128 similar frames.  One CTA of 128 threads per (frame, channel); a
@@ -905,6 +894,67 @@ k_simmodel_large(const float* __restrict__ Vsq, int T, int nch, const int* __res
     else if (n <= 64) simmodel_large<64>(vchan, vrow, s_list, n, out, t);
     else if (n <= 100) simmodel_large<100>(vchan, vrow, s_list, n, out, t);
     else simmodel_large<128>(vchan, vrow, s_list, n, out, t);
+}
+
+// k_simmodel_nyquist: the median of the Nyquist bin (the 1025th of a row) for lists of 1..128 frames, one THREAD
+// per (frame, channel).  Inside the per-frame CTAs that bin cost a whole extra pass of a selection network with a
+// single active lane (1/9 of the long-list kernel, 1/5 of the short-list one); here 32 frames share the pass.
+template <int N>
+__device__ __forceinline__ float nyquist_median_small(const float2* __restrict__ chan, size_t row,
+                                                      const int* __restrict__ list) {
+    float v[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        const float y = __ldg(&chan[(size_t)__ldg(list + s) * row]).y;
+        v[s] = __fmul_rn(y, y);
+    }
+    median_select<N>(v);
+    return (N & 1) ? fast_sqrt(v[(N - 1) / 2]) : 0.5f * (fast_sqrt(v[(N - 1) / 2]) + fast_sqrt(v[N / 2]));
+}
+template <int NS>
+__device__ __forceinline__ float nyquist_median_large(const float* __restrict__ vchan, size_t vrow,
+                                                      const int* __restrict__ list, int n) {
+    float v[NS];
+    const int lo = (NS - n) >> 1;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (s < n) v[s] = __ldg(vchan + (size_t)__ldg(list + s) * vrow + XPITCH);
+        else v[s] = (s - n) < lo ? -INFINITY : INFINITY;
+    }
+    median_select<NS>(v);
+    return (n & 1) ? fast_sqrt(v[NS / 2 - 1]) : 0.5f * (fast_sqrt(v[NS / 2 - 1]) + fast_sqrt(v[NS / 2]));
+}
+
+__global__ void __launch_bounds__(128)
+k_simmodel_nyquist(const float2* __restrict__ X, const float* __restrict__ Vsq, int T, int nch, const int* __restrict__ idx,
+                   const int* __restrict__ cnt, int number, int first_frame, float* __restrict__ model) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + first_frame;
+    if (j >= T) return;
+    const int item = blockIdx.y / nch, c = blockIdx.y - item * nch;
+    const int n = cnt[(size_t)item * T + j];
+    if (n < 1 || n > 128) return;  // empty lists are NaN rows already; longer ones take the shared-memory path
+    const int* __restrict__ list = idx + ((size_t)item * T + j) * (size_t)number;
+    float* __restrict__ out = model + (((size_t)item * nch + c) * (size_t)T + j) * PPITCH + XPITCH;
+    if (n <= 32) {
+        const size_t row = (size_t)nch * XPITCH;
+        const float2* __restrict__ chan = X + (size_t)item * T * row + (size_t)c * XPITCH;
+        switch (n) {
+#define REPET_CASE(N) case N: *out = nyquist_median_small<N>(chan, row, list); break;
+            REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+            REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+            REPET_CASE(15) REPET_CASE(16) REPET_CASE(17) REPET_CASE(18) REPET_CASE(19) REPET_CASE(20) REPET_CASE(21)
+            REPET_CASE(22) REPET_CASE(23) REPET_CASE(24) REPET_CASE(25) REPET_CASE(26) REPET_CASE(27) REPET_CASE(28)
+            REPET_CASE(29) REPET_CASE(30) REPET_CASE(31) REPET_CASE(32)
+#undef REPET_CASE
+        }
+        return;
+    }
+    const float* __restrict__ vchan = Vsq + ((size_t)item * T * nch + c) * PPITCH;
+    const size_t vrow = (size_t)nch * PPITCH;
+    if (n <= 48) *out = nyquist_median_large<48>(vchan, vrow, list, n);
+    else if (n <= 64) *out = nyquist_median_large<64>(vchan, vrow, list, n);
+    else if (n <= 100) *out = nyquist_median_large<100>(vchan, vrow, list, n);
+    else *out = nyquist_median_large<128>(vchan, vrow, list, n);
 }
 
 __global__ void __launch_bounds__(SIMMODEL_THREADS)
@@ -988,6 +1038,8 @@ int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_it
     dim3 grid(T - first_frame, n_items * nch);
     k_simmodel<<<grid, SIMMODEL_THREADS, smem, st>>>(X, Vsq, T, nch, idx, cnt, number, first_frame, model);
     if (number > 32) k_simmodel_large<<<grid, 128, 0, st>>>(Vsq, T, nch, idx, cnt, number, first_frame, model);
+    k_simmodel_nyquist<<<dim3((T - first_frame + 127) / 128, n_items * nch), 128, 0, st>>>(X, Vsq, T, nch, idx, cnt, number,
+                                                                                          first_frame, model);
     return 0;
 }
 
