@@ -33,36 +33,56 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 // multiply by -i
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
+// float64 flavour of the same plan (k_frames64: the similarity operand of REPET-SIM)
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }
 
-// 4-point DFT, natural order in and out.
-__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
+// 4-point DFT, natural order in and out.  V = float2 or double2.
+template <typename V>
+__device__ __forceinline__ void dft4(V& a0, V& a1, V& a2, V& a3) {
+    const V t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
     a0 = cadd(t0, t2);
     a2 = csub(t0, t2);
     // t1 +- (-i d): the cross terms stay scalar (no half swap needed)
-    a1 = make_float2(t1.x + d.y, t1.y - d.x);
-    a3 = make_float2(t1.x - d.y, t1.y + d.x);
+    a1 = V{t1.x + d.y, t1.y - d.x};
+    a3 = V{t1.x - d.y, t1.y + d.x};
 }
 
-#define REPET_SQRT1_2 0.70710678118654752440f
-#define REPET_COS_PI_8 0.92387953251128675613f
-#define REPET_SIN_PI_8 0.38268343236508977173f
+// constants in the component type of V (the float values are the correctly rounded doubles)
+template <typename V>
+struct Real;
+template <>
+struct Real<float2> {
+    using type = float;
+};
+template <>
+struct Real<double2> {
+    using type = double;
+};
+#define REPET_SQRT1_2 ((typename Real<V>::type)0.70710678118654752440)
+#define REPET_COS_PI_8 ((typename Real<V>::type)0.92387953251128675613)
+#define REPET_SIN_PI_8 ((typename Real<V>::type)0.38268343236508977173)
 
 // multiply by W_16^j for the j that occur in a 4x4 split (j = m*k1, m,k1 in 0..3)
-template <int J>
-__device__ __forceinline__ float2 mul_w16(float2 a) {
+template <int J, typename V>
+__device__ __forceinline__ V mul_w16(V a) {
     if (J == 0) return a;
-    if (J == 1) return cmul(a, make_float2(REPET_COS_PI_8, -REPET_SIN_PI_8));
-    if (J == 2) return make_float2((a.x + a.y) * REPET_SQRT1_2, (a.y - a.x) * REPET_SQRT1_2);
-    if (J == 3) return cmul(a, make_float2(REPET_SIN_PI_8, -REPET_COS_PI_8));
+    if (J == 1) return cmul(a, V{REPET_COS_PI_8, -REPET_SIN_PI_8});
+    if (J == 2) return V{(a.x + a.y) * REPET_SQRT1_2, (a.y - a.x) * REPET_SQRT1_2};
+    if (J == 3) return cmul(a, V{REPET_SIN_PI_8, -REPET_COS_PI_8});
     if (J == 4) return cmul_mi(a);
-    if (J == 6) return make_float2((a.y - a.x) * REPET_SQRT1_2, -(a.x + a.y) * REPET_SQRT1_2);
-    if (J == 9) return cmul(a, make_float2(-REPET_COS_PI_8, REPET_SIN_PI_8));
+    if (J == 6) return V{(a.y - a.x) * REPET_SQRT1_2, -(a.x + a.y) * REPET_SQRT1_2};
+    if (J == 9) return cmul(a, V{-REPET_COS_PI_8, REPET_SIN_PI_8});
     return a;
 }
 
 // 16-point DFT in registers, natural order in and out (n = n1*4 + m, k = k1 + 4*k').
-__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+template <typename V>
+__device__ __forceinline__ void dft16(V (&a)[16]) {
 #pragma unroll
     for (int m = 0; m < 4; ++m) dft4(a[m], a[4 + m], a[8 + m], a[12 + m]);
     // a[k1*4 + m] now holds u[m][k1]; twiddle by W_16^(m*k1)
@@ -78,20 +98,21 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) dft4(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
     // a[k1*4 + k'] holds X[k1 + 4*k']: transpose the 4x4 index to natural order
-    float2 t;
+    V t;
 #define REPET_SWAP(i, j) t = a[i]; a[i] = a[j]; a[j] = t;
     REPET_SWAP(1, 4) REPET_SWAP(2, 8) REPET_SWAP(3, 12) REPET_SWAP(6, 9) REPET_SWAP(7, 13) REPET_SWAP(11, 14)
 #undef REPET_SWAP
 }
 
 // 8-point DFT in registers, natural order in and out (n = n1*2 + m, k = k1 + 4*k').
-__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+template <typename V>
+__device__ __forceinline__ void dft8(V (&a)[8]) {
     dft4(a[0], a[2], a[4], a[6]);  // m = 0: u0[k1] in a[2*k1]
     dft4(a[1], a[3], a[5], a[7]);  // m = 1: u1[k1] in a[2*k1 + 1]
-    float2 u1_1 = make_float2((a[3].x + a[3].y) * REPET_SQRT1_2, (a[3].y - a[3].x) * REPET_SQRT1_2);   // W_8^1
-    float2 u1_2 = cmul_mi(a[5]);                                                                        // W_8^2
-    float2 u1_3 = make_float2((a[7].y - a[7].x) * REPET_SQRT1_2, -(a[7].x + a[7].y) * REPET_SQRT1_2);  // W_8^3
-    float2 u0_0 = a[0], u0_1 = a[2], u0_2 = a[4], u0_3 = a[6], u1_0 = a[1];
+    V u1_1 = V{(a[3].x + a[3].y) * REPET_SQRT1_2, (a[3].y - a[3].x) * REPET_SQRT1_2};   // W_8^1
+    V u1_2 = cmul_mi(a[5]);                                                             // W_8^2
+    V u1_3 = V{(a[7].y - a[7].x) * REPET_SQRT1_2, -(a[7].x + a[7].y) * REPET_SQRT1_2};  // W_8^3
+    V u0_0 = a[0], u0_1 = a[2], u0_2 = a[4], u0_3 = a[6], u1_0 = a[1];
     a[0] = cadd(u0_0, u1_0);
     a[4] = csub(u0_0, u1_0);
     a[1] = cadd(u0_1, u1_1);
@@ -118,12 +139,12 @@ struct FftPlan<2048> {
 };
 
 // DFT of R consecutive registers r[OFF .. OFF+R) of the 16-element array (natural order in and out)
-template <int R, int OFF>
-__device__ __forceinline__ void dft_slice(float2 (&r)[16]) {
+template <int R, int OFF, typename V>
+__device__ __forceinline__ void dft_slice(V (&r)[16]) {
     if constexpr (R == 16) {
         dft16(r);
     } else if constexpr (R == 8) {
-        float2 c[8];
+        V c[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) c[i] = r[OFF + i];
         dft8(c);
@@ -134,7 +155,7 @@ __device__ __forceinline__ void dft_slice(float2 (&r)[16]) {
     }
 }
 
-template <int N>
+template <int N, typename V = float2>
 struct Fft {
     static constexpr int SIZE = N;
     static constexpr int THREADS = N / 16;
@@ -142,7 +163,7 @@ struct Fft {
     static constexpr int R3 = 8;
     static constexpr int NB2 = 16 / R2;           // stage-2 butterflies per thread
     static constexpr int PITCH1 = THREADS + 1;    // y1 row pitch
-    static constexpr int BUF = 16 * PITCH1;       // float2 elements per exchange buffer (>= N)
+    static constexpr int BUF = 16 * PITCH1;       // V elements per exchange buffer (>= N)
     static constexpr int CCOLS = 2 * THREADS;     // output columns (residues mod 2T)
     static constexpr int TW1 = 15 * THREADS;      // entries of the stage-1 twiddle table
     static constexpr int TW2 = THREADS;           // entries of the stage-2 twiddle table [k2][m2]
@@ -151,15 +172,15 @@ struct Fft {
     // Per-thread constant twiddles of stage 1: W_N^(m*k1), k1 = 1..15, from the table
     // tw1g[(k1-1)*T + m] (built in double precision on the host, repet_abi.cu).
     struct Twiddle1 {
-        float2 w[15];
-        __device__ __forceinline__ void load(const float2* __restrict__ tw1g, int t) {
+        V w[15];
+        __device__ __forceinline__ void load(const V* __restrict__ tw1g, int t) {
 #pragma unroll
             for (int k1 = 1; k1 < 16; ++k1) w[k1 - 1] = __ldg(&tw1g[(k1 - 1) * THREADS + t]);
         }
     };
 
     // stage 1: r[n1] = x[n1*T + t] on entry; writes y1 to dst.
-    static __device__ __forceinline__ void stage1(float2 (&r)[16], const Twiddle1& tw, float2* __restrict__ dst, int t) {
+    static __device__ __forceinline__ void stage1(V (&r)[16], const Twiddle1& tw, V* __restrict__ dst, int t) {
         dft16(r);
         dst[t] = r[0];
 #pragma unroll
@@ -167,8 +188,8 @@ struct Fft {
     }
 
     template <int Q>
-    static __device__ __forceinline__ void stage2_one(float2 (&r)[16], const float2* __restrict__ src,
-                                                      float2* __restrict__ dst, const float2* __restrict__ s_tw2,
+    static __device__ __forceinline__ void stage2_one(V (&r)[16], const V* __restrict__ src,
+                                                      V* __restrict__ dst, const V* __restrict__ s_tw2,
                                                       int k1, int mb) {
         const int m2 = mb + (THREADS / 16) * Q;
 #pragma unroll
@@ -180,8 +201,8 @@ struct Fft {
     }
 
     // stage 2: reads y1 from src, writes y2 to dst.  s_tw2[k2*8 + m2] = W_T^(m2*k2).
-    static __device__ __forceinline__ void stage2(float2 (&r)[16], const float2* __restrict__ src,
-                                                  float2* __restrict__ dst, const float2* __restrict__ s_tw2, int t) {
+    static __device__ __forceinline__ void stage2(V (&r)[16], const V* __restrict__ src,
+                                                  V* __restrict__ dst, const V* __restrict__ s_tw2, int t) {
         const int k1 = t & 15, mb = t >> 4;
         stage2_one<0>(r, src, dst, s_tw2, k1, mb);
         if constexpr (NB2 > 1) stage2_one<(NB2 > 1 ? 1 : 0)>(r, src, dst, s_tw2, k1, mb);
@@ -201,12 +222,12 @@ struct Fft {
     }
 
     // stage 3: reads y2 from src; on exit r[h*8 + k3] = Z[out_column(t, h) + 2T*k3].
-    static __device__ __forceinline__ void stage3(float2 (&r)[16], const float2* __restrict__ src, int t) {
+    static __device__ __forceinline__ void stage3(V (&r)[16], const V* __restrict__ src, int t) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int pi = out_column(t, h);
-            const float2* col = src + (pi >> 4) * (R3 * 16) + (pi & 15);
-            float2 c[8];
+            const V* col = src + (pi >> 4) * (R3 * 16) + (pi & 15);
+            V c[8];
 #pragma unroll
             for (int m2 = 0; m2 < 8; ++m2) c[m2] = col[m2 * 16];
             dft8(c);
@@ -226,30 +247,30 @@ struct Fft {
     //   tstage1  DFT-16 over k1 for m = t
     // Per-thread constant twiddles of tstage2, from the stage-1 table tw1g[(k1-1)*T + m].
     struct TwiddleT {
-        float2 w[16];
-        __device__ __forceinline__ void load(const float2* __restrict__ tw1g, int t) {
+        V w[16];
+        __device__ __forceinline__ void load(const V* __restrict__ tw1g, int t) {
             const int k1 = t & 15, mb = t >> 4;
 #pragma unroll
             for (int q = 0; q < NB2; ++q)
 #pragma unroll
                 for (int n2 = 0; n2 < R2; ++n2) {
                     const int m = n2 * R3 + mb + (THREADS / 16) * q;
-                    w[q * R2 + n2] = k1 ? __ldg(&tw1g[(k1 - 1) * THREADS + m]) : make_float2(1.f, 0.f);
+                    w[q * R2 + n2] = k1 ? __ldg(&tw1g[(k1 - 1) * THREADS + m]) : V{1, 0};
                 }
         }
     };
 
-    static __device__ __forceinline__ void tstage3(float2 (&r)[16], float2* __restrict__ dst,
-                                                   const float2* __restrict__ s_tw2, int t) {
+    static __device__ __forceinline__ void tstage3(V (&r)[16], V* __restrict__ dst,
+                                                   const V* __restrict__ s_tw2, int t) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int pi = out_column(t, h);
-            float2 c[8];
+            V c[8];
 #pragma unroll
             for (int k3 = 0; k3 < 8; ++k3) c[k3] = r[h * 8 + k3];
             dft8(c);
-            float2* col = dst + (pi >> 4) * (R3 * 16) + (pi & 15);
-            const float2* twc = s_tw2 + (pi >> 4) * R3;
+            V* col = dst + (pi >> 4) * (R3 * 16) + (pi & 15);
+            const V* twc = s_tw2 + (pi >> 4) * R3;
             col[0] = c[0];
 #pragma unroll
             for (int m2 = 1; m2 < 8; ++m2) col[m2 * 16] = cmul(c[m2], twc[m2]);
@@ -257,8 +278,8 @@ struct Fft {
     }
 
     template <int Q>
-    static __device__ __forceinline__ void tstage2_one(float2 (&r)[16], const float2* __restrict__ src,
-                                                       float2* __restrict__ dst, const TwiddleT& tw, int k1, int mb) {
+    static __device__ __forceinline__ void tstage2_one(V (&r)[16], const V* __restrict__ src,
+                                                       V* __restrict__ dst, const TwiddleT& tw, int k1, int mb) {
         const int m2 = mb + (THREADS / 16) * Q;
 #pragma unroll
         for (int k2 = 0; k2 < R2; ++k2) r[Q * R2 + k2] = src[(k2 * R3 + m2) * 16 + k1];
@@ -267,8 +288,8 @@ struct Fft {
         for (int n2 = 0; n2 < R2; ++n2) dst[k1 * PITCH1 + n2 * R3 + m2] = cmul(r[Q * R2 + n2], tw.w[Q * R2 + n2]);
     }
 
-    static __device__ __forceinline__ void tstage2(float2 (&r)[16], const float2* __restrict__ src,
-                                                   float2* __restrict__ dst, const TwiddleT& tw, int t) {
+    static __device__ __forceinline__ void tstage2(V (&r)[16], const V* __restrict__ src,
+                                                   V* __restrict__ dst, const TwiddleT& tw, int t) {
         const int k1 = t & 15, mb = t >> 4;
         tstage2_one<0>(r, src, dst, tw, k1, mb);
         if constexpr (NB2 > 1) tstage2_one<(NB2 > 1 ? 1 : 0)>(r, src, dst, tw, k1, mb);
@@ -278,7 +299,7 @@ struct Fft {
         }
     }
 
-    static __device__ __forceinline__ void tstage1(float2 (&r)[16], const float2* __restrict__ src, int t) {
+    static __device__ __forceinline__ void tstage1(V (&r)[16], const V* __restrict__ src, int t) {
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) r[k1] = src[k1 * PITCH1 + t];
         dft16(r);

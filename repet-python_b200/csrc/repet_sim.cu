@@ -66,130 +66,144 @@ void launch_normalize(cudaStream_t st, const float* V, int n_rows, double* An64,
 // value -- enough to flip near-tied candidates on a long track -- so the operand of the similarity
 // (An64, and the TF32 operands rounded from it) is rebuilt here with a float64 transform; the fp32
 // spectra of k_stft are only used for the mask and the resynthesis (tolerance 1e-4).
-// One CTA per frame: both channels packed into one complex transform (z = w (xL + i xR)), radix-4
-// Stockham autosort between two shared-memory buffers, Hermitian split, magnitudes by hypot (as
-// np.abs), channel mean, float64 norm, and the three operand formats written in one pass.
+// A CTA of N/16 threads walks 8 consecutive frames: both channels packed into one complex transform
+// (z = w (xL + i xR)) run through the register-blocked 16 x R2 x 8 plan of fft_core.cuh instantiated for
+// double2 (a thread ends up holding Z[k] and Z[N-k]: the Hermitian split needs no exchange), magnitudes,
+// channel mean, float64 norm, and the three operand formats written from registers.
 // An all-zero frame gives 0/0 = NaN as in the reference (quirk Q18).
 // ------------------------------------------------------------------------------------------
-constexpr int F64_THREADS = 256;
+using F64 = Fft<WIN_N, double2>;  // the frame transform of fft_core.cuh in float64: same plan, same ownership
+constexpr int F64_FRAMES = 8;     // consecutive frames per CTA (twiddles stay in registers)
+
+// one bin of the channel-mean magnitude from Z[k] and Z[N-k] of the packed transform (equal for k = 0, N/2)
+template <int NCH>
+__device__ __forceinline__ double mean_magnitude64(double2 zk, double2 zm) {
+    // sqrt(re^2 + im^2): within 1.5 ulp of np.abs's hypot, no risk of overflow for audio-scale spectra
+    if (NCH == 1) return sqrt(fma(zk.x, zk.x, zk.y * zk.y));
+    const double lr = 0.5 * (zk.x + zm.x), li = 0.5 * (zk.y - zm.y), rr = 0.5 * (zk.x - zm.x), ri = 0.5 * (zk.y + zm.y);
+    return 0.5 * (sqrt(fma(lr, lr, li * li)) + sqrt(fma(rr, rr, ri * ri)));
+}
+
+__device__ __forceinline__ void write_operands(size_t row, int k, double a, double* __restrict__ An64,
+                                               float* __restrict__ An32, float* __restrict__ An32lo, int round_tf32) {
+    An64[row * APITCH64 + k] = a;
+    if (!An32) return;
+    float f = (float)a;
+    if (round_tf32) {  // round-to-nearest TF32 here, so the tensor core's operand truncation is exact
+        uint32_t bits;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(f));
+        const float hi = __uint_as_float(bits);
+        if (An32lo) {  // 3xTF32: the residual, itself rounded to TF32 (a ~ hi + lo to 2^-22)
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"((float)(a - (double)hi)));
+            An32lo[row * KPAD + k] = __uint_as_float(bits);
+        }
+        f = hi;
+    }
+    An32[row * KPAD + k] = f;
+}
 
 template <int NCH>
-__global__ void __launch_bounds__(F64_THREADS)
+__global__ void __launch_bounds__(F64::THREADS)
 k_frames64(const float* __restrict__ audio, const double* __restrict__ audio64, Geom g,
            const double* __restrict__ window64, const double2* __restrict__ tw64, double* __restrict__ An64,
            float* __restrict__ An32, float* __restrict__ An32lo, int round_tf32) {
     extern __shared__ __align__(16) unsigned char s_raw64[];
     double2* bufA = reinterpret_cast<double2*>(s_raw64);
-    double2* bufB = bufA + WIN_N;
-    __shared__ double s_red[F64_THREADS / 32];
+    double2* bufB = bufA + F64::BUF;
+    double2* s_tw2 = bufB + F64::BUF;
+    __shared__ double s_red[F64::THREADS / 32];
     const int t = threadIdx.x;
-    const int j = blockIdx.x, item = blockIdx.y;
-    const int gitem = g.item0 + item;
-    const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
-    const long long start = g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
-    const long long base = (long long)(j - 1 + g.frame_shift) * HOP;
-    for (int n = t; n < WIN_N; n += F64_THREADS) {
-        const long long idx = base + n;
-        double xl = 0.0, xr = 0.0;
-        if (idx >= 0 && idx < g.S) {
-            if (audio64) {  // float64 (samples, channels) of one clip: the reference's own input
-                xl = audio64[(start + idx) * NCH];
-                if (NCH == 2) xr = audio64[(start + idx) * NCH + 1];
-            } else {
-                xl = (double)audio[start + idx];
-                if (NCH == 2) xr = (double)audio[start + g.chan_stride + idx];
-            }
-        }
-        const double w = window64[n];
-        bufA[n] = make_double2(xl * w, xr * w);
-    }
-    __syncthreads();
-    double2* src = bufA;
-    double2* dst = bufB;
+    const int item = blockIdx.y;
+    const int j0 = blockIdx.x * F64_FRAMES, j1 = min(j0 + F64_FRAMES, g.T);
     // W_N^i for any i < N from the half table: W_N^(i + N/2) = -W_N^i
     auto twiddle = [&](int i) {
         const double2 w = tw64[i & (WIN_N / 2 - 1)];
         return (i & (WIN_N / 2)) ? make_double2(-w.x, -w.y) : w;
     };
-    auto cmul64 = [](double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); };
-    int ns = 1;
-    for (; ns * 4 <= WIN_N; ns <<= 2) {  // radix-4 Stockham stages
-        const int tw_step = WIN_N / (4 * ns);
-        for (int q = t; q < WIN_N / 4; q += F64_THREADS) {
-            const int k = q & (ns - 1);
-            const double2 a0 = src[q];
-            const double2 a1 = cmul64(src[q + WIN_N / 4], twiddle(k * tw_step));
-            const double2 a2 = cmul64(src[q + WIN_N / 2], twiddle(2 * k * tw_step));
-            const double2 a3 = cmul64(src[q + 3 * (WIN_N / 4)], twiddle(3 * k * tw_step));
-            const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
-            const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
-            const int o = ((q - k) << 2) + k;
-            dst[o] = make_double2(s02.x + s13.x, s02.y + s13.y);
-            dst[o + ns] = make_double2(d02.x + d13.y, d02.y - d13.x);      // a0 - i a1 - a2 + i a3
-            dst[o + 2 * ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
-            dst[o + 3 * ns] = make_double2(d02.x - d13.y, d02.y + d13.x);  // a0 + i a1 - a2 - i a3
-        }
-        __syncthreads();
-        double2* tmp = src;
-        src = dst;
-        dst = tmp;
-    }
-    if (ns < WIN_N) {  // one radix-2 stage left when log2 N is odd
-        for (int q = t; q < WIN_N / 2; q += F64_THREADS) {
-            const int k = q & (ns - 1);
-            const double2 a = src[q];
-            const double2 b = cmul64(src[q + WIN_N / 2], twiddle(k * (WIN_N / (2 * ns))));
-            const int o = ((q - k) << 1) + k;
-            dst[o] = make_double2(a.x + b.x, a.y + b.y);
-            dst[o + ns] = make_double2(a.x - b.x, a.y - b.y);
-        }
-        __syncthreads();
-        double2* tmp = src;
-        src = dst;
-        dst = tmp;
-    }
-    // src holds Z = FFT(w (xL + i xR)); XL[k] = (Z[k] + conj Z[N-k])/2, XR[k] = (Z[k] - conj Z[N-k])/(2i)
-    double* v = reinterpret_cast<double*>(dst);
-    double sum = 0.0;
-    for (int k = t; k < NBIN; k += F64_THREADS) {
-        const double2 zk = src[k];
-        double mag;
-        if (NCH == 2) {
-            const double2 zm = src[(WIN_N - k) & (WIN_N - 1)];
-            const double ml = hypot(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-            const double mr = hypot(0.5 * (zk.x - zm.x), 0.5 * (zk.y + zm.y));
-            mag = 0.5 * (ml + mr);
-        } else {
-            mag = hypot(zk.x, zk.y);
-        }
-        v[k] = mag;
-        sum = fma(mag, mag, sum);
-    }
+    F64::Twiddle1 tw;  // W_N^(t k1), k1 = 1..15
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((t & 31) == 0) s_red[t >> 5] = sum;
+    for (int k1 = 1; k1 < 16; ++k1) tw.w[k1 - 1] = twiddle((t * k1) & (WIN_N - 1));
+    if (t < F64::TW2) s_tw2[t] = twiddle((16 * (t >> 3) * (t & 7)) & (WIN_N - 1));  // W_T^(m2 k2) at [k2*8 + m2]
+    const int gitem = g.item0 + item;
+    const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
+    const long long start = g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
     __syncthreads();
-    double total = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        double2 r[16];
+        const long long base = (long long)(j - 1 + g.frame_shift) * HOP + t;
 #pragma unroll
-    for (int i = 0; i < F64_THREADS / 32; ++i) total += s_red[i];
-    const double norm = sqrt(total);
-    const size_t row = (size_t)item * g.T + j;
-    for (int k = t; k < KPAD; k += F64_THREADS) {
-        const double a = k < NBIN ? v[k] / norm : 0.0;
-        if (k < APITCH64) An64[row * APITCH64 + k] = a;
-        if (An32) {
-            float f = (float)a;
-            if (round_tf32) {
-                uint32_t bits;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(f));
-                const float hi = __uint_as_float(bits);
-                if (An32lo) {
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"((float)(a - (double)hi)));
-                    An32lo[row * KPAD + k] = __uint_as_float(bits);
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const long long idx = base + n1 * F64::THREADS;
+            double xl = 0.0, xr = 0.0;
+            if (idx >= 0 && idx < g.S) {
+                if (audio64) {  // float64 (samples, channels) of one clip: the reference's own input
+                    xl = audio64[(start + idx) * NCH];
+                    if (NCH == 2) xr = audio64[(start + idx) * NCH + 1];
+                } else {
+                    xl = (double)__ldg(audio + start + idx);
+                    if (NCH == 2) xr = (double)__ldg(audio + start + g.chan_stride + idx);
                 }
-                f = hi;
             }
-            An32[row * KPAD + k] = f;
+            const double w = __ldg(window64 + n1 * F64::THREADS + t);
+            r[n1] = make_double2(xl * w, xr * w);
+        }
+        F64::stage1(r, tw, bufA, t);
+        __syncthreads();
+        F64::stage2(r, bufA, bufB, s_tw2, t);
+        __syncthreads();
+        F64::stage3(r, bufB, t);
+        // r[h*8 + k3] = Z[out_column(t, h) + 2T k3]; the mirror bin N - k sits in the other column at 7 - k3
+        // (thread 0 owns the self-mirrored columns 0 and T).  Bins 0 .. N/2 of the thread:
+        double mag[9];
+        int bin[9];
+        int nb = 8;
+        if (t != 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k3 = 0; k3 < 4; ++k3) {
+                    bin[h * 4 + k3] = (h == 0 ? t : F64::CCOLS - t) + F64::CCOLS * k3;
+                    mag[h * 4 + k3] = mean_magnitude64<NCH>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3]);
+                }
+            bin[8] = 0;
+            mag[8] = 0.0;
+        } else {
+            bin[0] = 0;
+            mag[0] = mean_magnitude64<NCH>(r[0], r[0]);
+#pragma unroll
+            for (int k3 = 1; k3 < 4; ++k3) {
+                bin[k3] = F64::CCOLS * k3;
+                mag[k3] = mean_magnitude64<NCH>(r[k3], r[8 - k3]);
+            }
+#pragma unroll
+            for (int k3 = 0; k3 < 4; ++k3) {
+                bin[4 + k3] = F64::THREADS + F64::CCOLS * k3;
+                mag[4 + k3] = mean_magnitude64<NCH>(r[8 + k3], r[8 + 7 - k3]);
+            }
+            bin[8] = WIN_N / 2;
+            mag[8] = mean_magnitude64<NCH>(r[4], r[4]);
+            nb = 9;
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sum = fma(mag[i], mag[i], sum);  // mag[8] = 0 where unused
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if ((t & 31) == 0) s_red[t >> 5] = sum;
+        __syncthreads();
+        double total = 0.0;
+#pragma unroll
+        for (int i = 0; i < F64::THREADS / 32; ++i) total += s_red[i];
+        const double inv_norm = 1.0 / sqrt(total);  // all-zero frame: 0 * inf = NaN, the reference's 0/0 (quirk Q18)
+        const size_t row = (size_t)item * g.T + j;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            if (i < nb) write_operands(row, bin[i], mag[i] * inv_norm, An64, An32, An32lo, round_tf32);
+        // zero padding of the rows: bins NBIN .. APITCH64-1 (float64) and NBIN .. KPAD-1 (fp32 operands)
+        if (NBIN + t < APITCH64) An64[row * APITCH64 + NBIN + t] = 0.0;
+        if (An32 && NBIN + t < KPAD) {
+            An32[row * KPAD + NBIN + t] = 0.f;
+            if (round_tf32 && An32lo) An32lo[row * KPAD + NBIN + t] = 0.f;
         }
     }
 }
@@ -197,18 +211,18 @@ k_frames64(const float* __restrict__ audio, const double* __restrict__ audio64, 
 void launch_frames64(cudaStream_t st, const float* audio, const double* audio64, Geom g, int nch,
                      const double* window64, const double2* tw64, double* An64, float* An32, float* An32lo,
                      int round_tf32) {
-    const size_t smem = (size_t)2 * WIN_N * sizeof(double2);
+    const size_t smem = (size_t)(2 * F64::BUF + F64::TW2) * sizeof(double2);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_frames64<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_frames64<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    dim3 grid(g.T, g.n_items);
+    dim3 grid((g.T + F64_FRAMES - 1) / F64_FRAMES, g.n_items);
     if (nch == 2)
-        k_frames64<2><<<grid, F64_THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
+        k_frames64<2><<<grid, F64::THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
     else
-        k_frames64<1><<<grid, F64_THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
+        k_frames64<1><<<grid, F64::THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
 }
 
 // ------------------------------------------------------------------------------------------
