@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-clips", type=int, default=0, help="clips of the CPU baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the GPU's NUMA-local CPUs")
     ap.add_argument("--workspace-mb", type=int, default=0, help="per-chunk workspace cap of the library (0 = default)")
     ap.add_argument("--tune", default="", help="comma separated knob=value pairs for repet_set_tuning (experiments)")
     return ap.parse_args()
@@ -260,9 +261,29 @@ def ncu_traffic(kernel, clips_per_launch):
         return None
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process (and the pinned host buffers it allocates next: first touch) to the CPUs NVML reports
+    as local to the GPU.  With several ranks per box the host-buffer copies otherwise cross the socket
+    interconnect.  Best effort: returns a description, or why it was skipped."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = len(os.sched_getaffinity(0))
+        if after == 0:
+            raise RuntimeError("empty affinity")
+        return "bound to %d of %d cpus (NVML affinity of GPU %d)" % (after, before, gpu_index)
+    except Exception as exc:  # not fatal: containers may forbid it
+        return "not bound: %r" % (exc,)
+
+
 def run_b200_arm(args, rank, local_rank, world):
     import repet_synth
 
+    numa = "disabled" if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
     B = args.clips_per_gpu
     # 1) synthesise this rank's clips on the host BEFORE CUDA is initialised (fork pool)
     t_gen = time.perf_counter()
@@ -429,7 +450,7 @@ def run_b200_arm(args, rank, local_rank, world):
             "dtype": "f32", "data": "synthetic", "config": config_dict(args), "clocks": clocks,
             "gpu_launches": int(launches), "roofline": roofline,
             "periods_sample": periods_first[:8].tolist(), "synthesis_seconds": t_gen,
-            "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,
+            "host_enqueue_ms_per_step": 1e3 * t_host / args.steps, "numa": numa,
         }
         if e2e_ms is not None:
             line["e2e"] = {"value": audio_seconds_per_step * args.steps / (e2e_max_ms / 1e3), "unit": UNIT,
