@@ -209,6 +209,7 @@ int repet_set_tuning(const char* name, int value) {
     else if (key == "beat_parts") g_repet_tuning.beat_parts = value;
     else if (key == "simgemm_tc") g_repet_tuning.simgemm_tc = value;
     else if (key == "sim_frames64") g_repet_tuning.sim_frames64 = value;
+    else if (key == "copy_chunk_mb") g_repet_tuning.copy_chunk_mb = value;
     else if (key == "cert_rel_ppm") g_repet_tuning.cert_rel_ppm = value;
     else return REPET_E_INVALID_ARG;
     return REPET_OK;

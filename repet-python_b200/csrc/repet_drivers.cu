@@ -540,8 +540,11 @@ int batch_host(repet_handle* h, int kind, const void* audio_any, bool pcm16, int
     CU(cudaSetDevice(h->device));
     const size_t clip_elems = (size_t)nch * (size_t)S;
     const size_t clip_bytes = clip_elems * sizeof(float);
-    // copy granularity: about 256 MB per slot, two slots in flight in each direction
-    int Gc = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_clips, ((size_t)256 << 20) / std::max<size_t>(1, clip_bytes)));
+    // copy granularity: about copy_chunk_mb per slot, two slots in flight in each direction.  Small slots shorten
+    // the fill and drain of the H2D -> compute -> D2H pipeline (the first upload and the last download overlap
+    // nothing); the kernels have ~10x headroom over PCIe, so their efficiency on small chunks does not matter
+    const size_t slot_target = (size_t)std::max(8, g_tuning.copy_chunk_mb) << 20;
+    int Gc = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_clips, slot_target / std::max<size_t>(1, clip_bytes)));
     Plan plan;
     if ((rc = make_plan(h, kind, p, nch, S, Gc, &plan))) return rc;
     const int Gw = std::min(Gc, chunk_clips(h, plan, Gc));

@@ -22,6 +22,7 @@ struct repet_tuning {
     int beat_parts = 0;      // 0 = pick from the batch size
     int cert_rel_ppm = 0;    // period certification window in ppm of the best value (0 = CERT_REL = 100 ppm)
     int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
+    int copy_chunk_mb = 128; // host-buffer entry points: megabytes per copy slot (pipeline granularity)
     int sim_frames64 = 1;    // similarity operand from the float64 front end (k_frames64); 0 = from k_stft's fp32 magnitudes
 };
 extern repet_tuning g_repet_tuning;
