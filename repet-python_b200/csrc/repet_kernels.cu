@@ -62,6 +62,7 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
     __shared__ float2 s_bufA[FF::BUF];
     __shared__ float2 s_bufB[FF::BUF];
     __shared__ float2 s_tw2[FF::TW2];
+    __shared__ float s_win[WIN_N];  // half the window: the 1/2 of the channel split is folded in here
     const int t = threadIdx.x;
     const int item = blockIdx.y;
     const int j0 = blockIdx.x * K;
@@ -69,58 +70,48 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
     s_tw2[t] = tb.tw2[t];
     FF::Twiddle1 tw;
     tw.load(tb.tw1, t);
-    float wv[16];  // half the window: the 1/2 of the channel split is folded in here
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) wv[n1] = 0.5f * __ldg(&window[n1 * FF::THREADS + t]);
+    for (int n1 = 0; n1 < 16; ++n1) s_win[n1 * FF::THREADS + t] = 0.5f * __ldg(&window[n1 * FF::THREADS + t]);
     const int gitem = g.item0 + item;
     const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
     const float* __restrict__ a0 = audio + g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
     const float* __restrict__ a1 = a0 + g.chan_stride;
-    // first half of the first frame (raw samples); afterwards it is the previous frame's second half
-    float cl[8], cr[8];
-    {
-        const long long base = (long long)(j0 - 1 + g.frame_shift) * HOP + t;
-#pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) {
-            const long long idx = base + n1 * FF::THREADS;
-            const bool ok = idx >= 0 && idx < g.S;
-            cl[n1] = ok ? __ldg(a0 + idx) : 0.f;
-            cr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
-        }
-    }
-    __syncthreads();
-    for (int j = j0; j < j1; ++j) {
-        float2 r[16];
-        const long long base = (long long)(j + g.frame_shift) * HOP + t;  // second half of frame j
-        // pull the next frame's new half (2 x 4 KB) towards L2 while this frame is transformed
-        constexpr int LINES = HOP / 32;  // 128-byte lines of one channel's half frame
-        if (t < NCH * LINES && j + 1 < j1) {
-            const long long nxt = base - t + HOP + (t % LINES) * 32;
-            if (nxt < g.S) prefetch_l2((t < LINES ? a0 : a1) + nxt);
-        }
-        float nl[8], nr[8];
-        if (base - t + HOP <= g.S) {  // whole half frame inside the signal: no bounds checks
+    // The window lives in shared memory so that the registers can hold TWO half frames: the first half of the
+    // current frame (= the previous frame's second half) and the second half, which is fetched one frame ahead --
+    // its global-load latency hides behind the previous frame's transform instead of stalling the window multiply.
+    float cl[8], cr[8], nl[8], nr[8];
+    auto fetch_half = [&](int j, float (&dl)[8], float (&dr)[8]) {  // second half of frame j
+        const long long base = (long long)(j + g.frame_shift) * HOP + t;
+        if (base - t >= 0 && base - t + HOP <= g.S) {  // whole half frame inside the signal: no bounds checks
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
-                nl[n1] = __ldg(a0 + base + n1 * FF::THREADS);
-                nr[n1] = NCH == 2 ? __ldg(a1 + base + n1 * FF::THREADS) : 0.f;
+                dl[n1] = __ldg(a0 + base + n1 * FF::THREADS);
+                dr[n1] = NCH == 2 ? __ldg(a1 + base + n1 * FF::THREADS) : 0.f;
             }
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
                 const long long idx = base + n1 * FF::THREADS;
-                const bool ok = idx < g.S;
-                nl[n1] = ok ? __ldg(a0 + idx) : 0.f;
-                nr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
+                const bool ok = idx >= 0 && idx < g.S;
+                dl[n1] = ok ? __ldg(a0 + idx) : 0.f;
+                dr[n1] = (NCH == 2 && ok) ? __ldg(a1 + idx) : 0.f;
             }
         }
+    };
+    fetch_half(j0 - 1, cl, cr);  // first half of the first frame
+    fetch_half(j0, nl, nr);
+    __syncthreads();
+    for (int j = j0; j < j1; ++j) {
+        float2 r[16];
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
-            r[n1] = make_float2(wv[n1] * cl[n1], wv[n1] * cr[n1]);
-            r[8 + n1] = make_float2(wv[8 + n1] * nl[n1], wv[8 + n1] * nr[n1]);
+            const float w_lo = s_win[n1 * FF::THREADS + t], w_hi = s_win[(8 + n1) * FF::THREADS + t];
+            r[n1] = make_float2(w_lo * cl[n1], w_lo * cr[n1]);
+            r[8 + n1] = make_float2(w_hi * nl[n1], w_hi * nr[n1]);
             cl[n1] = nl[n1];
             cr[n1] = nr[n1];
         }
+        if (j + 1 < j1) fetch_half(j + 1, nl, nr);  // consumed one transform from now
         FF::stage1(r, tw, s_bufA, t);
         __syncthreads();
         FF::stage2(r, s_bufA, s_bufB, s_tw2, t);
@@ -928,6 +919,24 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             if (exists(b0 + d))
                 bulk_load(s_ring[d], Xitem + (size_t)row_of(b0 + d) * (NCH * XPITCH), ROW_BYTES, &s_full[d]);
     }
+    // model rows (L2 resident) of frame jc, 8 bins per channel: issued one frame ahead, right after the previous
+    // frame's masks have consumed these registers, so their latency hides behind that frame's transform
+    float ml[2][4], mr[2][4];
+    auto load_model = [&](int jc) {
+        if (!MASKED || !exists(jc)) return;
+        const int q = row_of(jc) % p;
+        const float* __restrict__ lrow = model + (((size_t)item * NCH + 0) * pmax + q) * PPITCH;
+        const float* __restrict__ rrow = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k3 = 0; k3 < 4; ++k3) {
+                const int k = FF::out_column(t, h) + FF::CCOLS * k3;
+                ml[h][k3] = __ldg(&lrow[k]);
+                if (NCH == 2) mr[h][k3] = __ldg(&rrow[k]);
+            }
+    };
+    load_model(b0);
     uint32_t phase = 0;  // bit s = parity of the next completion of slot s
     for (int jc = b0; jc <= b1; ++jc) {
         const int j = row_of(jc);
@@ -939,23 +948,15 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             for (int i = 0; i < 16; ++i) r[i] = make_float2(0.f, 0.f);
             if (t == 0 && exists(jc + 2))
                 bulk_load(s_ring[slot], Xitem + (size_t)row_of(jc + 2) * (NCH * XPITCH), ROW_BYTES, &s_full[slot]);
+            load_model(jc + 1);
         } else {
-        // model rows first (L2 resident): their latency hides behind the wait for the spectra
-        float ml[2][4], mr[2][4];
+        // the model rows of this frame were fetched while the previous frame was transformed (load_model)
         const float* __restrict__ ml_row = nullptr;
         const float* __restrict__ mr_row = nullptr;
         if (MASKED) {
             const int q = j % p;
             ml_row = model + (((size_t)item * NCH + 0) * pmax + q) * PPITCH;
             mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int k3 = 0; k3 < 4; ++k3) {
-                    const int k = FF::out_column(t, h) + FF::CCOLS * k3;
-                    ml[h][k3] = __ldg(&ml_row[k]);
-                    if (NCH == 2) mr[h][k3] = __ldg(&mr_row[k]);
-                }
         }
         float2* __restrict__ ring = s_ring[slot];
         mbar_wait(&s_full[slot], (phase >> slot) & 1u);
@@ -1016,6 +1017,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
         r[13] = t0 ? zm[1][2] : zm[0][2];
         r[14] = t0 ? zm[1][1] : zm[0][1];
         r[15] = t0 ? zm[1][0] : zm[0][0];
+        load_model(jc + 1);
         __syncthreads();  // every thread has read its spectra: the slot becomes the y2 exchange buffer
         FF::tstage3(r, ring, s_tw2, t);
         __syncthreads();
