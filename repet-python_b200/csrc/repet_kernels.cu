@@ -922,9 +922,11 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     // model rows (L2 resident) of frame jc, 8 bins per channel: issued one frame ahead, right after the previous
     // frame's masks have consumed these registers, so their latency hides behind that frame's transform
     float ml[2][4], mr[2][4];
+    int q_cur = 0, q_next = 0;  // model row (phase) of the frame being processed / of the one prefetched
     auto load_model = [&](int jc) {
         if (!MASKED || !exists(jc)) return;
         const int q = row_of(jc) % p;
+        q_next = q;
         const float* __restrict__ lrow = model + (((size_t)item * NCH + 0) * pmax + q) * PPITCH;
         const float* __restrict__ rrow = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
 #pragma unroll
@@ -939,6 +941,7 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     load_model(b0);
     uint32_t phase = 0;  // bit s = parity of the next completion of slot s
     for (int jc = b0; jc <= b1; ++jc) {
+        q_cur = q_next;
         const int j = row_of(jc);
         const int slot = (jc - b0) & 1;
         float2 r[16];
@@ -953,10 +956,9 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
         // the model rows of this frame were fetched while the previous frame was transformed (load_model)
         const float* __restrict__ ml_row = nullptr;
         const float* __restrict__ mr_row = nullptr;
-        if (MASKED) {
-            const int q = j % p;
-            ml_row = model + (((size_t)item * NCH + 0) * pmax + q) * PPITCH;
-            mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q) * PPITCH;
+        if (MASKED) {  // (only thread 0 dereferences these, for the Nyquist bin)
+            ml_row = model + (((size_t)item * NCH + 0) * pmax + q_cur) * PPITCH;
+            mr_row = model + (((size_t)item * NCH + (NCH - 1)) * pmax + q_cur) * PPITCH;
         }
         float2* __restrict__ ring = s_ring[slot];
         mbar_wait(&s_full[slot], (phase >> slot) & 1u);
