@@ -902,6 +902,9 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
     s_tw2[t] = tb.tw2[t];
     typename FF::TwiddleT tw;
     tw.load(tb.tw1, t);
+    // 1 / (N * COLA gain) rides on the second-stage twiddles: every output passes through exactly one of them
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tw.w[i] = make_float2(tw.w[i].x * scale, tw.w[i].y * scale);
     const int gitem = g.item0 + item;
     const int clip = gitem / g.seg_per_clip, sg = gitem - clip * g.seg_per_clip;
     float* __restrict__ o0 = out + g.first_offset + (long long)clip * g.clip_stride + (long long)sg * g.seg_stride;
@@ -1029,15 +1032,15 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
             bulk_load(ring, Xitem + (size_t)row_of(jc + 2) * (NCH * XPITCH), ROW_BYTES, &s_full[slot]);
         FF::tstage1(r, s_y1, t);
         }
-        // r[n1] = (N*yR, N*yL) at frame sample n = n1*T + t: n1 < 8 completes block jc - 1, the rest is carried
+        // r[n1] = (yR, yL) / COLA gain at frame sample n = n1*T + t: n1 < 8 completes block jc - 1, the rest is carried
         if (jc > b0) {
             const long long blk = (long long)(jc - 1) * HOP;
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
                 const long long m = blk + n1 * FF::THREADS + t;
                 if (m < g.S) {
-                    o0[m] = (carry_l[n1] + r[n1].y) * scale;
-                    if (NCH == 2) o1[m] = (carry_r[n1] + r[n1].x) * scale;
+                    o0[m] = carry_l[n1] + r[n1].y;
+                    if (NCH == 2) o1[m] = carry_r[n1] + r[n1].x;
                 }
             }
         }
