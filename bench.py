@@ -174,7 +174,7 @@ def config_dict(args, sample_clips=None):
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML every ~5 ms DURING the timed region."""
+    """SM clock and throttle reasons sampled through NVML every few ms DURING the timed region."""
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
@@ -221,7 +221,7 @@ class ClockSampler:
             except Exception as exc:  # pragma: no cover
                 self.error = repr(exc)
                 break
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def stop(self):
         self.running = False
