@@ -1203,6 +1203,7 @@ void launch_adaptive_model(cudaStream_t st, const float2* X, int n_items, int T,
 // the falling half of triang(2*overlap) and adds itself scaled by the rising half over its
 // first `overlap` samples, and simply adds beyond.
 // ------------------------------------------------------------------------------------------
+template <bool VEC4>
 __global__ void k_xfade(const float* __restrict__ seg_main, const float* __restrict__ seg_last, int n_seg, int seg_len,
                         int last_len, int step, int nch, int S, float* __restrict__ out) {
     // 32-bit index arithmetic (a clip has fewer than 2^31 samples); 4 consecutive samples per thread
@@ -1214,10 +1215,37 @@ __global__ void k_xfade(const float* __restrict__ seg_main, const float* __restr
     const float* __restrict__ main_base = seg_main + ((size_t)clip * (n_seg - 1) * nch + c) * (size_t)seg_len;
     const float* __restrict__ last_base = seg_last + ((size_t)clip * nch + c) * (size_t)last_len;
     float* __restrict__ dst = out + ((size_t)clip * nch + c) * (size_t)S;
-    // the covering segments of the 4 samples differ at most at segment boundaries: compute per sample,
-    // but share the divisions
     const int q_hi = u0 / step;
     const int q_lo = u0 < seg_len ? -1 : (u0 - seg_len) / step;
+    if (VEC4 && u0 + 3 < S) {
+        // step, segment length and every buffer length are multiples of 4 samples: the 4 samples of the thread sit
+        // in the same segments, on the same side of every overlap boundary, and every access is a 16-byte one
+        const int sg_hi = min(q_hi, n_seg - 1);
+        const int sg_lo = min(u0 < seg_len ? 0 : q_lo + 1, n_seg - 1);
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sg = sg_lo; sg <= sg_hi; ++sg) {
+            const int i = u0 - sg * step;
+            const float4 x = __ldg(reinterpret_cast<const float4*>(
+                sg < n_seg - 1 ? main_base + (size_t)sg * nch * seg_len + i : last_base + i));
+            if (sg > 0 && i < ov) {
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+                float v[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float up = (float)(2 * (i + e) + 1) * inv;               // triang(2 ov)[i]
+                    const float down = (float)(2 * (ov - 1 - (i + e)) + 1) * inv;  // triang(2 ov)[ov + i]
+                    v[e] = v[e] * down + xs[e] * up;
+                }
+                val = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+                val = make_float4(val.x + x.x, val.y + x.y, val.z + x.z, val.w + x.w);
+            }
+        }
+        *reinterpret_cast<float4*>(dst + u0) = val;
+        return;
+    }
+    // the covering segments of the 4 samples differ at most at segment boundaries: compute per sample,
+    // but share the divisions
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int u = u0 + e;
@@ -1245,7 +1273,12 @@ __global__ void k_xfade(const float* __restrict__ seg_main, const float* __restr
 void launch_xfade(cudaStream_t st, const float* seg_main, const float* seg_last, int n_clips, int n_seg, int seg_len,
                   int last_len, int step, int nch, long long S, float* out) {
     dim3 grid((unsigned)((S + 1023) / 1024), n_clips * nch);
-    k_xfade<<<grid, 256, 0, st>>>(seg_main, seg_last, n_seg, seg_len, last_len, step, nch, (int)S, out);
+    // 16-byte path: every offset a thread forms is a multiple of 4 samples (the workspace slices are 256-byte aligned)
+    const bool vec4 = step % 4 == 0 && seg_len % 4 == 0 && last_len % 4 == 0 && S % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(seg_main) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(seg_last) & 15) == 0;
+    if (vec4) k_xfade<true><<<grid, 256, 0, st>>>(seg_main, seg_last, n_seg, seg_len, last_len, step, nch, (int)S, out);
+    else k_xfade<false><<<grid, 256, 0, st>>>(seg_main, seg_last, n_seg, seg_len, last_len, step, nch, (int)S, out);
 }
 
 // ------------------------------------------------------------------------------------------
