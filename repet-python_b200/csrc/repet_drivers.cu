@@ -93,6 +93,7 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
         float2* X = bump.take<float2>((size_t)g_items * s.T * nch * XPITCH);
         float* P = bump.take<float>((size_t)g_items * s.T * PPITCH);
         const bool blocked = s.n_blocks > 1;
+        const int beat_L = blocked ? BEAT_L : beat_transform_length(s.T, s.lag_hi);
         const int total_parts = s.n_blocks * s.n_parts;
         float* psd = bump.take<float>((size_t)g_items * total_parts * BEAT_L);
         float* psd_im = blocked ? bump.take<float>((size_t)g_items * total_parts * BEAT_L) : nullptr;
@@ -112,12 +113,12 @@ int period_pipeline(repet_handle* h, const float* audio, Geom gin, float* out, G
                 launch_beat_blocked(st, P, g_items, s.T, s.block_frames, s.lag_hi, tables(h), psd, psd_im, s.n_blocks,
                                     s.n_parts, s.f_per_part);
             else
-                launch_beat(st, P, g_items, s.T, 0, s.T, 0, 1, tables(h), psd, s.n_parts, s.f_per_part);
+                launch_beat(st, P, g_items, s.T, 0, s.T, 0, 1, tables(h), psd, s.n_parts, s.f_per_part, beat_L);
         }
         {
             Timed timed(h, REPET_K_PERIODS, 3);  // k_periods, k_period_certify, k_period_finalize
             launch_periods(st, psd, psd_im, g_items, total_parts, s.T, (double)NBIN, p->period_lo, s.lag_hi, 0, 0, nullptr,
-                           0, periods_dev + first, nullptr, cert);
+                           0, periods_dev + first, nullptr, cert, beat_L);
             launch_period_certify(st, P, g_items, s.T, 0, s.T, 0, 1, cert, cert_val, periods_dev + first);
         }
         {
@@ -449,6 +450,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         Geom geom = clip_geom(g, nch, plan.S, T);
         geom.first_offset = (long long)clip0 * geom.clip_stride;
         const int K = pick_frames_per_cta(h, (long long)g * T);
+        const int beat_L = beat_transform_length(plan.seg_frames, plan.lag_hi);
         {
             Timed timed(h, REPET_K_STFT);
             launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, P, P_POWER, K);
@@ -457,12 +459,12 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
             // segment i spans frames [i - left_pad, i - left_pad + L) (zero outside), repet.py:1177-1198
             Timed timed(h, REPET_K_BEAT);
             launch_beat(st, P, g, T, -plan.left_pad, plan.seg_frames, plan.step_frames, plan.n_beat_seg, tables(h), psd,
-                        plan.beat_parts, plan.beat_f_per_part);
+                        plan.beat_parts, plan.beat_f_per_part, beat_L);
         }
         {
             Timed timed(h, REPET_K_PERIODS, 3);
             launch_periods(st, psd, nullptr, g * plan.n_beat_seg, plan.beat_parts, plan.seg_frames, (double)NBIN, plan.p.period_lo,
-                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr, cert);
+                           plan.lag_hi, 0, 0, nullptr, 0, seg_period, nullptr, cert, beat_L);
             launch_period_certify(st, P, g * plan.n_beat_seg, T, -plan.left_pad, plan.seg_frames, plan.step_frames,
                                   plan.n_beat_seg, cert, cert_val, seg_period);
         }

@@ -164,7 +164,7 @@ inline int frames_of(int64_t n_samples) {  // repet.py:1018-1028 with N = 2H
 }
 inline const float* window_of(repet_handle* h) { return h->win[WIN_SLOT].window; }
 inline FftTables tables(repet_handle* h) {
-    return FftTables{h->win[WIN_SLOT].tw1, h->win[WIN_SLOT].tw2, h->win[2].tw1, h->win[2].tw2};
+    return FftTables{h->win[WIN_SLOT].tw1, h->win[WIN_SLOT].tw2, h->win[2].tw1, h->win[2].tw2, h->win[1].tw1, h->win[1].tw2};
 }
 
 inline int check_common(repet_handle* h, const repet_params* p, int n_channels) {

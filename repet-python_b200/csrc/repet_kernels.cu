@@ -206,9 +206,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(TF::THREADS)
+// BL = transform length: 2048, or 1024 when rows + max lag fit (10 s segments of `extended` / `adaptive`: less
+// than half the butterflies).  Partials are written with a pitch of BEAT_L floats either way.
+template <int BL>
+__global__ void __launch_bounds__(BL / 16)
 k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step, int n_seg, FftTables tb,
        float* __restrict__ psd_part, int n_parts, int f_per_part, int TP) {
+    using TF = Fft<BL>;
     extern __shared__ __align__(16) unsigned char s_raw[];
     float2* s_bufA = reinterpret_cast<float2*>(s_raw);
     float2* s_bufB = s_bufA + TF::BUF;
@@ -220,9 +224,9 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
     const int ts = t_first + sg * seg_step;
     const int f_begin = blockIdx.x * f_per_part;
     const int f_end = min(NBIN, f_begin + f_per_part);
-    s_tw2[t] = tb.tw2_t[t];
-    TF::Twiddle1 tw;
-    tw.load(tb.tw1_t, t);
+    s_tw2[t] = (BL == 2048 ? tb.tw2_t : tb.tw2_t1k)[t];
+    typename TF::Twiddle1 tw;
+    tw.load(BL == 2048 ? tb.tw1_t : tb.tw1_t1k, t);
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -275,23 +279,31 @@ k_beat(const float* __restrict__ P, int T, int t_first, int t_len, int seg_step,
         for (int k3 = 0; k3 < 8; ++k3) out[TF::out_column(t, h) + TF::CCOLS * k3] = acc[h * 8 + k3];
 }
 
+template <int BL>
 static size_t beat_smem_bytes(int t_len, int* TP_out) {
     int TP = ((t_len + 7) / 8) * 8 + 8;
     *TP_out = TP;
-    return (size_t)(2 * TF::BUF + TF::TW2) * sizeof(float2) + (size_t)2 * TP * sizeof(float4);
+    return (size_t)(2 * Fft<BL>::BUF + Fft<BL>::TW2) * sizeof(float2) + (size_t)2 * TP * sizeof(float4);
 }
 
-void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
-                 FftTables tb, float* psd_part, int n_parts, int f_per_part) {
+template <int BL>
+static void go_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
+                    FftTables tb, float* psd_part, int n_parts, int f_per_part) {
     int TP;
-    size_t smem = beat_smem_bytes(t_len, &TP);
+    size_t smem = beat_smem_bytes<BL>(t_len, &TP);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(k_beat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_beat<BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     dim3 grid(n_parts, n_items * n_seg);
-    k_beat<<<grid, TF::THREADS, smem, st>>>(P, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part, TP);
+    k_beat<BL><<<grid, BL / 16, smem, st>>>(P, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part, TP);
+}
+
+void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
+                 FftTables tb, float* psd_part, int n_parts, int f_per_part, int L) {
+    if (L == 1024) go_beat<1024>(st, P, n_items, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part);
+    else go_beat<2048>(st, P, n_items, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,34 +316,36 @@ void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_firs
 __global__ void __launch_bounds__(256)
 k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part_im, int n_parts, int t_len,
           double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* __restrict__ beat_out,
-          int beat_pitch, int* __restrict__ period, double* __restrict__ stats, int* __restrict__ cert, double cert_rel) {
+          int beat_pitch, int* __restrict__ period, double* __restrict__ stats, int* __restrict__ cert, double cert_rel, int L) {
+    // L = length of the time-axis transforms that produced the partials (1024 for short segments, else 2048);
+    // the partials keep a pitch of L floats either way
     extern __shared__ __align__(16) unsigned char s_raw_periods[];
-    double* s_cos = reinterpret_cast<double*>(s_raw_periods);  // [BEAT_L]      cos(2 pi k / L)
-    double* s_b = s_cos + BEAT_L;                              // [BEAT_L]      partial sums, then b[l]
-    double* s_psd = s_b + BEAT_L;                              // [BEAT_L/2+1]  symmetric part of Re G
-    double* s_im = s_psd + BEAT_L / 2 + 1;                     // [BEAT_L/2+1]  antisymmetric part of Im G
+    double* s_cos = reinterpret_cast<double*>(s_raw_periods);  // [L]      cos(2 pi k / L)
+    double* s_b = s_cos + L;                              // [L]      partial sums, then b[l]
+    double* s_psd = s_b + L;                              // [L/2+1]  symmetric part of Re G
+    double* s_im = s_psd + L / 2 + 1;                     // [L/2+1]  antisymmetric part of Im G
     const int t = threadIdx.x;
     const int bi = blockIdx.x;
-    for (int k = t; k < BEAT_L; k += 256) {
+    for (int k = t; k < L; k += 256) {
         double a = 0.0;
         const float* __restrict__ src = psd_part + (size_t)bi * n_parts * BEAT_L + k;
         for (int part = 0; part < n_parts; ++part) a += (double)src[(size_t)part * BEAT_L];
         s_b[k] = a;
-        s_cos[k] = cospi((double)k / (double)(BEAT_L / 2));
+        s_cos[k] = cospi((double)k / (double)(L / 2));
     }
     __syncthreads();
-    for (int k = t; k <= BEAT_L / 2; k += 256) s_psd[k] = 0.5 * (s_b[k] + s_b[(BEAT_L - k) & (BEAT_L - 1)]);
+    for (int k = t; k <= L / 2; k += 256) s_psd[k] = 0.5 * (s_b[k] + s_b[(L - k) & (L - 1)]);
     __syncthreads();
     if (psd_part_im) {
         // blocked cross-spectrum G = sum conj(A) C: r[l] = (1/L) sum_k Re G cos - Im G sin, G Hermitian
-        for (int k = t; k < BEAT_L; k += 256) {
+        for (int k = t; k < L; k += 256) {
             double a = 0.0;
             const float* __restrict__ src = psd_part_im + (size_t)bi * n_parts * BEAT_L + k;
             for (int part = 0; part < n_parts; ++part) a += (double)src[(size_t)part * BEAT_L];
             s_b[k] = a;
         }
         __syncthreads();
-        for (int k = t; k <= BEAT_L / 2; k += 256) s_im[k] = 0.5 * (s_b[k] - s_b[(BEAT_L - k) & (BEAT_L - 1)]);
+        for (int k = t; k <= L / 2; k += 256) s_im[k] = 0.5 * (s_b[k] - s_b[(L - k) & (L - 1)]);
         __syncthreads();
     }
     int l0 = out_lo, l1 = out_hi;
@@ -347,11 +361,11 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
             // lane-dependent stride.  Its rounding (~1e-12 relative for the lags in range) is far inside the
             // 100 ppm window below which k_period_certify re-decides the argmax from exact sums.
             double sn, c;
-            sincospi((double)l / (double)(BEAT_L / 2), &sn, &c);
+            sincospi((double)l / (double)(L / 2), &sn, &c);
             const double c2 = 2.0 * c;
             double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
             if (psd_part_im) {
-                for (int k = BEAT_L / 2 - 1; k >= 1; --k) {
+                for (int k = L / 2 - 1; k >= 1; --k) {
                     const double b0 = fma(c2, b1, s_psd[k] - b2);
                     const double d0 = fma(c2, d1, s_im[k] - d2);
                     b2 = b1;
@@ -360,7 +374,7 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
                     d1 = d0;
                 }
             } else {
-                for (int k = BEAT_L / 2 - 1; k >= 1; --k) {
+                for (int k = L / 2 - 1; k >= 1; --k) {
                     const double b0 = fma(c2, b1, s_psd[k] - b2);
                     b2 = b1;
                     b1 = b0;
@@ -368,16 +382,16 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
             }
             s = fma(b1, c, -b2) - d1 * sn;
         } else if (psd_part_im) {
-            for (int k = 1; k < BEAT_L / 2; ++k) {
-                const int ph = (k * l) & (BEAT_L - 1);
+            for (int k = 1; k < L / 2; ++k) {
+                const int ph = (k * l) & (L - 1);
                 s = fma(s_psd[k], s_cos[ph], s);
-                s = fma(-s_im[k], s_cos[(ph - BEAT_L / 4) & (BEAT_L - 1)], s);  // sin(x) = cos(x - pi/2)
+                s = fma(-s_im[k], s_cos[(ph - L / 4) & (L - 1)], s);  // sin(x) = cos(x - pi/2)
             }
         } else {
-            for (int k = 1; k < BEAT_L / 2; ++k) s = fma(s_psd[k], s_cos[(k * l) & (BEAT_L - 1)], s);
+            for (int k = 1; k < L / 2; ++k) s = fma(s_psd[k], s_cos[(k * l) & (L - 1)], s);
         }
-        s = 2.0 * s + s_psd[0] + ((l & 1) ? -s_psd[BEAT_L / 2] : s_psd[BEAT_L / 2]);
-        s_b[l] = s / (double)BEAT_L / ((double)(t_len - l) * norm_rows);
+        s = 2.0 * s + s_psd[0] + ((l & 1) ? -s_psd[L / 2] : s_psd[L / 2]);
+        s_b[l] = s / (double)L / ((double)(t_len - l) * norm_rows);
     }
     __syncthreads();
     if (beat_out)
@@ -433,7 +447,7 @@ k_periods(const float* __restrict__ psd_part, const float* __restrict__ psd_part
 
 void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_part_im, int n_beat_items, int n_parts,
                     int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
-                    int beat_pitch, int* period, double* stats, int* cert) {
+                    int beat_pitch, int* period, double* stats, int* cert, int L) {
     const size_t smem = (size_t)(2 * BEAT_L + 2 * (BEAT_L / 2 + 1)) * sizeof(double);
     static bool configured = false;
     if (!configured) {
@@ -442,7 +456,7 @@ void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_par
     }
     k_periods<<<n_beat_items, 256, smem, st>>>(psd_part, psd_part_im, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo,
                                               out_hi, beat_out, beat_pitch, period, stats, cert,
-                                              g_tuning.cert_rel_ppm > 0 ? 1e-6 * g_tuning.cert_rel_ppm : CERT_REL);
+                                              g_tuning.cert_rel_ppm > 0 ? 1e-6 * g_tuning.cert_rel_ppm : CERT_REL, L);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -65,6 +65,8 @@ struct FftTables {
     const float2* tw2;    //                  [R2][8]      W_(N/16)^(m2*k2)
     const float2* tw1_t;  // time-axis transform (2048): [15][128]
     const float2* tw2_t;  //                              [16][8]
+    const float2* tw1_t1k;  // time-axis transform of short segments (1024): [15][64]
+    const float2* tw2_t1k;  //                                               [8][8]
 };
 
 enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2, P_MIXDOWN = 3 };  // MIXDOWN: |STFT(mean_c x)| only, no X
@@ -79,12 +81,14 @@ void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const flo
 // k_beat: P rows [t_first, t_first + t_len) of every item (zero outside [0, T)) -> partial PSD sums
 // psd_part[item][part][2048]
 void launch_beat(cudaStream_t st, const float* P, int n_items, int T, int t_first, int t_len, int seg_step, int n_seg,
-                 FftTables tb, float* psd_part, int n_parts, int f_per_part);
+                 FftTables tb, float* psd_part, int n_parts, int f_per_part, int L = BEAT_L);
+// transform length for a beat item of `rows` frames and lags below `max_lag`: 1024 when it fits, else BEAT_L
+inline int beat_transform_length(int rows, int max_lag) { return rows + max_lag - 1 <= 1024 ? 1024 : BEAT_L; }
 
 // k_periods: partial PSDs -> beat spectrum b[l] (optional) and argmax period per beat item (fp64)
 void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_part_im, int n_beat_items, int n_parts,
                     int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
-                    int beat_pitch, int* period, double* stats, int* cert);
+                    int beat_pitch, int* period, double* stats, int* cert, int L = BEAT_L);
 // near-tied period candidates re-decided in float64 (cert: [item][1 + CERT_MAX] ints written by k_periods)
 constexpr int CERT_MAX = 8;
 constexpr double CERT_REL = 1e-4;
