@@ -96,7 +96,14 @@ def original_batch(audio_signals, sampling_frequency):
     Outputs:
         background_signals: float32 array of the same shape
         repeating_periods: int32 array (number_clips,), in time frames
+
+    A list / tuple of (number_channels, number_samples_i) arrays of DIFFERENT lengths is accepted too: the clips
+    are grouped by shape (never padded: a clip's period range depends on its length) and the outputs come back as
+    a list of backgrounds and an int32 array of periods, in input order.
     """
+    if isinstance(audio_signals, (list, tuple)):
+        backgrounds, periods = _host.driver_batch_ragged("original", audio_signals, sampling_frequency, _tunables())
+        return backgrounds, np.array([int(p[0]) for p in periods], dtype=np.int32)
     return _host.original_batch(audio_signals, sampling_frequency, _tunables())
 
 

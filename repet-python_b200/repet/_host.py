@@ -599,6 +599,37 @@ def driver_batch(driver, audio, sampling_frequency, tunables, handle=None):
     return background, ints
 
 
+def ragged_groups(shapes):
+    """Group clip indices by (channels, samples): clips of equal shape go through one batch call.  Pure host
+    logic (the groups are returned in order of first appearance, indices ascending inside a group)."""
+    groups = {}
+    for index, shape in enumerate(shapes):
+        if len(shape) != 2:
+            raise ValueError("every clip must have shape (channels, samples)")
+        groups.setdefault((int(shape[0]), int(shape[1])), []).append(index)
+    return list(groups.items())
+
+
+def driver_batch_ragged(driver, clips, sampling_frequency, tunables, handle=None):
+    """A batch of clips of DIFFERENT lengths (a list of (C, S_i) float32 arrays): clips are never padded
+    -- a clip's frame count, period range and periods depend on its length (repet.py:165-173) -- but grouped
+    by shape, one batch call per group.  Returns (list of backgrounds, list of integer outputs) in input order."""
+    clips = [np.asarray(c, dtype=np.float32) for c in clips]
+    backgrounds = [None] * len(clips)
+    integers = [None] * len(clips)
+    for (channels, samples), members in ragged_groups([c.shape for c in clips]):
+        stacked = np.stack([clips[i] for i in members]) if members else np.zeros((0, channels, samples), np.float32)
+        if driver == "original":
+            background, ints = original_batch(stacked, sampling_frequency, tunables, handle=handle)
+            ints = ints[:, None]
+        else:
+            background, ints = driver_batch(driver, stacked, sampling_frequency, tunables, handle=handle)
+        for slot, index in enumerate(members):
+            backgrounds[index] = background[slot]
+            integers[index] = ints[slot]
+    return backgrounds, integers
+
+
 def beatspectrogram(audio_spectrogram, segment_length, segment_step, handle=None):
     """_beatspectrogram (repet.py:1161-1206): (F, T) -> float64 (segment_length, T).  The device
     computes the beat spectrum of every segment; the column replication (including the all-zero

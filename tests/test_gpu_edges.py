@@ -115,3 +115,18 @@ def test_clip_shorter_than_the_period_range_raises(repet):
         repet.original(np.full((3000, 2), 0.01), FS)
     with pytest.raises(ValueError):
         repet.original_batch(np.zeros((2, 2, 3000), dtype=np.float32), FS)
+
+
+def test_ragged_batch_equals_single_calls(repet):
+    """Clips of different lengths in one call: grouped by shape, never padded (a clip's frame count and period
+    range depend on its length), outputs in input order."""
+    lengths = [7 * FS, 9 * FS + 11, 7 * FS, 5 * FS + 3, 9 * FS + 11]
+    clips = [repet_synth.make_clip(700 + i, n) for i, n in enumerate(lengths)]
+    backgrounds, periods = repet.original_batch(clips, FS)
+    assert len(backgrounds) == len(clips) and periods.shape == (len(clips),)
+    for i, clip in enumerate(clips):
+        single, period = repet.original_batch(clip[None], FS)
+        assert backgrounds[i].shape == clip.shape
+        assert np.array_equal(backgrounds[i], single[0]) and int(periods[i]) == int(period[0])
+        _, det = oracle.original(clip.T.astype(np.float64), FS, return_details=True)
+        assert int(periods[i]) == det["period"]

@@ -182,3 +182,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_ragged_batches_are_grouped_by_shape_not_padded():
+    import repet
+
+    shapes = [(2, 1000), (2, 1200), (2, 1000), (1, 1000), (2, 1200), (2, 1000)]
+    groups = repet._host.ragged_groups(shapes)
+    assert groups == [((2, 1000), [0, 2, 5]), ((2, 1200), [1, 4]), ((1, 1000), [3])]
+    assert sorted(i for _, members in groups for i in members) == list(range(len(shapes)))
+    assert repet._host.ragged_groups([]) == []
+    with pytest.raises(ValueError):
+        repet._host.ragged_groups([(2, 1000, 1)])
