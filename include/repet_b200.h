@@ -164,6 +164,22 @@ int repet_simonline_batch(repet_handle* h, const float* audio, int n_clips, int 
 int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels, const repet_params* p,
                         double* background, int32_t* lists_host, int lists_capacity);
 
+/* Stateful stream of the online REPET-SIM (repet.py:712-911 fed block by block).  The
+ * stream keeps its sample history (the last buffer_length seconds) in device memory: a block costs one upload
+ * of the new samples and one download of the samples that became final.  repet_simonline_block takes the next
+ * n_samples x n_channels float64 samples (host) and writes the background samples that have become final (every
+ * frame covering them is complete: a latency of one hop); repet_simonline_flush returns the rest, zero-padding
+ * the last frame as the reference does.  The concatenated outputs equal repet_simonline_f64 on the whole signal
+ * (same ring-slot order, quirk Q6; nothing before frame buffer_frames-1, quirk Q5).  `capacity` = samples per
+ * channel the background buffer holds (a block can release at most n_samples + one hop of them); *n_out = samples
+ * per channel written.  One stream per handle at a time (calls are stream-ordered on the handle). */
+typedef struct repet_stream repet_stream;
+int repet_simonline_open(repet_handle* h, const repet_params* p, int n_channels, repet_stream** out);
+int repet_simonline_block(repet_stream* s, const double* block, int64_t n_samples, double* background, int64_t capacity,
+                          int64_t* n_out);
+int repet_simonline_flush(repet_stream* s, double* background, int64_t capacity, int64_t* n_out);
+int repet_simonline_close(repet_stream* s);
+
 /* ---- by-products of a separation (README.md:64-81 of the reference) ---------------------- */
 /* One call for the reference's documented usage: background = method(audio) (method 0 original, 1 extended,
  * 2 adaptive, 3 sim, 4 simonline), foreground = audio - background (README.md:68), and the three display

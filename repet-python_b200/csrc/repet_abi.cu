@@ -299,6 +299,163 @@ int repet_simonline_f64(repet_handle* h, const double* audio, int64_t n_samples,
     return dispatch_f64(h, KIND_SIMONLINE, audio, n_samples, n_channels, p, background, lists_host, lists_capacity);
 }
 
+/* ---- stateful online REPET-SIM stream (repet_simonline_block) -------------------------- */
+}  // extern "C"
+
+struct repet_stream {
+    repet_handle* h = nullptr;
+    repet_params p;
+    int channels = 0;
+    int64_t received = 0;       // samples taken so far
+    int64_t emitted = 0;        // background samples handed out so far
+    int64_t frame0 = 0;         // first frame whose samples are still held (sample frame0 * H)
+    int64_t held = 0;           // samples held in d_hist (from sample frame0 * H on)
+    int64_t capacity = 0;       // samples d_hist / d_out can hold
+    double* d_hist = nullptr;   // device: the sample history, float64 (samples, channels)
+    double* d_out = nullptr;    // device: the background of the window analysed last / scratch for compaction
+};
+
+namespace {
+
+int stream_reserve(repet_stream* s, int64_t samples) {
+    repet_handle* h = s->h;
+    if (samples <= s->capacity) return REPET_OK;
+    const int64_t cap = std::max<int64_t>(samples + samples / 2, 1 << 16);
+    double *hist = nullptr, *out = nullptr;
+    CU(cudaMalloc(&hist, (size_t)cap * s->channels * sizeof(double)));
+    if (cudaMalloc(&out, (size_t)cap * s->channels * sizeof(double)) != cudaSuccess) {
+        cudaFree(hist);
+        return fail(h, REPET_E_OOM, "out of device memory for the stream history");
+    }
+    if (s->held > 0)
+        CU(cudaMemcpyAsync(hist, s->d_hist, (size_t)s->held * s->channels * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(s->d_hist);
+    cudaFree(s->d_out);
+    s->d_hist = hist;
+    s->d_out = out;
+    s->capacity = cap;
+    return REPET_OK;
+}
+
+// Emit background samples [emitted, final_until): analyse the window of frames that cover them together with
+// their similarity history (buffer_frames - 1 frames back), with the ring-slot order of the whole stream
+// (online_frame_base, quirk Q6).  `window_end` = one past the last sample the window may read.
+int stream_advance(repet_stream* s, int64_t final_until, int64_t window_end, double* background, int64_t capacity,
+                   int64_t* n_out) {
+    repet_handle* h = s->h;
+    *n_out = 0;
+    if (final_until <= s->emitted) return REPET_OK;
+    const int64_t H = s->p.step_length, B = s->p.buffer_frames;
+    const int64_t count = final_until - s->emitted;
+    if (count > capacity) return fail(h, REPET_E_INVALID_ARG, "background buffer too small for the samples that became final");
+    const int64_t first_block = s->emitted / H;
+    const int64_t first_needed = std::max<int64_t>(0, first_block - 1);  // block b mixes frames b-1 and b
+    int64_t first_frame = std::max<int64_t>(0, first_needed - (B - 1));   // ... and their similarity history
+    first_frame = std::max(first_frame, s->frame0);
+    const int64_t lo = (first_frame - s->frame0) * H;
+    const int64_t window = window_end - first_frame * H;
+    const repet_entry* e = entry_for(h, &s->p);
+    if (!e) return REPET_E_UNSUPPORTED;
+    repet_params p = s->p;
+    p.online_frame_base = (int32_t)first_frame;
+    int rc = e->single_f64_dev(h, KIND_SIMONLINE, s->d_hist + lo * s->channels, window, s->channels, &p, s->d_out);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(background, s->d_out + (s->emitted - first_frame * H) * s->channels,
+                       (size_t)count * s->channels * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    s->emitted = final_until;
+    *n_out = count;
+    // drop the samples no later window will need (compaction through the scratch buffer: the ranges overlap)
+    const int64_t keep_frame = std::max<int64_t>(0, s->emitted / H - 1 - (B - 1));
+    if (keep_frame > s->frame0) {
+        const int64_t drop = (keep_frame - s->frame0) * H;
+        const int64_t rest = s->held - drop;
+        if (rest > 0) {
+            CU(cudaMemcpyAsync(s->d_out, s->d_hist + drop * s->channels, (size_t)rest * s->channels * sizeof(double),
+                               cudaMemcpyDeviceToDevice, h->stream));
+            std::swap(s->d_hist, s->d_out);
+        }
+        s->held = std::max<int64_t>(rest, 0);
+        s->frame0 = keep_frame;
+    }
+    return REPET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int repet_simonline_open(repet_handle* h, const repet_params* p, int n_channels, repet_stream** out) {
+    if (!h || !out) return REPET_E_INVALID_ARG;
+    *out = nullptr;
+    if (!p) return fail(h, REPET_E_INVALID_ARG, "params is null");
+    if (!entry_for(h, p)) return REPET_E_UNSUPPORTED;
+    if (n_channels < 1 || n_channels > 2) return fail(h, REPET_E_UNSUPPORTED, "1 or 2 channels supported");
+    if (p->buffer_frames < 1) return fail(h, REPET_E_INVALID_ARG, "buffer_length must cover at least one frame");
+    repet_stream* s = new repet_stream();
+    s->h = h;
+    s->p = *p;
+    s->p.online_frame_base = 0;
+    s->channels = n_channels;
+    *out = s;
+    return REPET_OK;
+}
+
+int repet_simonline_block(repet_stream* s, const double* block, int64_t n_samples, double* background, int64_t capacity,
+                          int64_t* n_out) {
+    if (!s || !n_out) return REPET_E_INVALID_ARG;
+    repet_handle* h = s->h;
+    *n_out = 0;
+    if (n_samples < 0 || (n_samples > 0 && !block)) return fail(h, REPET_E_INVALID_ARG, "bad block");
+    CU(cudaSetDevice(h->device));
+    int rc = stream_reserve(s, s->held + n_samples);
+    if (rc) return rc;
+    if (n_samples > 0) {
+        CU(cudaMemcpyAsync(s->d_hist + s->held * s->channels, block, (size_t)n_samples * s->channels * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));  // the caller may reuse `block` as soon as this returns
+    }
+    s->held += n_samples;
+    s->received += n_samples;
+    const int64_t N = s->p.window_length, H = s->p.step_length, B = s->p.buffer_frames;
+    if (s->received < N) return REPET_OK;
+    const int64_t last_complete = (s->received - N) / H;
+    const int64_t final_until = (last_complete + 1) * H;
+    if (last_complete < B - 1) {
+        // nothing is synthesised before frame buffer_frames - 1 (quirk Q5): the final samples are zeros
+        const int64_t count = std::max<int64_t>(0, final_until - s->emitted);
+        if (count > capacity) return fail(h, REPET_E_INVALID_ARG, "background buffer too small for the samples that became final");
+        if (count > 0) std::memset(background, 0, (size_t)count * s->channels * sizeof(double));
+        s->emitted = std::max(s->emitted, final_until);
+        *n_out = count;
+        return REPET_OK;
+    }
+    return stream_advance(s, final_until, last_complete * H + N, background, capacity, n_out);
+}
+
+int repet_simonline_flush(repet_stream* s, double* background, int64_t capacity, int64_t* n_out) {
+    if (!s || !n_out) return REPET_E_INVALID_ARG;
+    repet_handle* h = s->h;
+    *n_out = 0;
+    if (s->received <= s->emitted) return REPET_OK;
+    const int64_t N = s->p.window_length, H = s->p.step_length, B = s->p.buffer_frames;
+    if (s->received < (B - 2) * H + N)
+        return fail(h, REPET_E_INVALID_ARG, "operands could not be broadcast together (signal shorter than the buffer)");
+    CU(cudaSetDevice(h->device));
+    return stream_advance(s, s->received, s->received, background, capacity, n_out);
+}
+
+int repet_simonline_close(repet_stream* s) {
+    if (!s) return REPET_OK;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->h->stream);
+    cudaFree(s->d_hist);
+    cudaFree(s->d_out);
+    delete s;
+    return REPET_OK;
+}
+
 int repet_separate_f64(repet_handle* h, int method, const double* audio, int64_t n_samples, int n_channels,
                        const repet_params* p, double* background, double* foreground, float* spectrograms,
                        int32_t* ints_host, int ints_capacity) {

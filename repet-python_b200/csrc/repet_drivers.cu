@@ -686,10 +686,50 @@ int single_f64(repet_handle* h, int kind, const double* audio, int64_t S, int nc
     return REPET_OK;
 }
 
+// float64 (samples, channels) in and out, both already on the DEVICE; stream-ordered, no synchronisation.
+// The stateful simonline stream keeps its sample history in device memory and runs its windows through here.
+int single_f64_dev(repet_handle* h, int kind, const double* d_audio, int64_t S, int nch, const repet_params* p,
+                   double* d_background) {
+    int rc = check_common(h, p, nch);
+    if (rc) return rc;
+    if (!d_audio || !d_background || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    CU(cudaSetDevice(h->device));
+    Plan plan;
+    if ((rc = make_plan(h, kind, p, nch, S, 1, &plan))) return rc;
+    const size_t n = (size_t)S * nch;
+    const size_t need = align_up((size_t)plan.ints_per_clip * sizeof(int32_t)) + 2 * align_up(n * sizeof(float)) +
+                        plan.bytes_per_clip;
+    if ((rc = ensure_arena(h, need))) return rc;
+    Bump bump(h->arena);
+    int32_t* ints = bump.take<int32_t>(plan.ints_per_clip);
+    float* in32 = bump.take<float>(n);
+    float* out32 = bump.take<float>(n);
+    unsigned char* ws = h->arena + bump.off;
+    cudaStream_t st = h->stream;
+    {
+        Timed timed(h, REPET_K_CONVERT);
+        launch_f64_interleaved_to_planar(st, d_audio, S, nch, in32);
+    }
+    h->f64_audio = d_audio;
+    rc = run_plan(h, plan, in32, 1, out32, ints, ws, plan.bytes_per_clip);
+    h->f64_audio = nullptr;
+    if (rc) return rc;
+    {
+        Timed timed(h, REPET_K_CONVERT);
+        launch_planar_to_f64_interleaved(st, out32, S, nch, d_background);
+    }
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
 }  // namespace
 
 namespace repet {
 
+int drv_single_f64_dev(repet_handle* h, int kind, const double* d_audio, int64_t n_samples, int n_channels,
+                       const repet_params* p, double* d_background) {
+    return single_f64_dev(h, kind, d_audio, n_samples, n_channels, p, d_background);
+}
 int drv_batch_dev(repet_handle* h, int kind, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                   const repet_params* p, float* background, int32_t* ints_dev, int32_t* ints_host) {
     return batch_dev(h, kind, audio, n_clips, n_channels, n_samples, p, background, ints_dev, ints_host, nullptr);

@@ -15,6 +15,7 @@ int drv_separate_f64(repet_handle*, int, const double*, int64_t, int, const repe
                      int32_t*, int64_t);
 int drv_spectrogram_dev(repet_handle*, const float*, int, int, int64_t, const repet_params*, float*);
 int drv_foreground_dev(repet_handle*, const float*, const float*, int64_t, float*);
+int drv_single_f64_dev(repet_handle*, int, const double*, int64_t, int, const repet_params*, double*);
 
 // ---------------------------------------------------------------------------------------------
 // helpers
@@ -415,7 +416,7 @@ const repet_entry* entry_table() {
     static const repet_entry table = {WIN_N,         drv_batch_dev,  drv_batch_host,      drv_single_f64,     hlp_stft,
                                       hlp_istft,     hlp_beat_common, hlp_mask,           hlp_adaptivemask,   hlp_beatspectrogram,
                                       hlp_selfsimilarity, hlp_periods, hlp_similarity,    hlp_localmaxima,    hlp_simmask,
-                                      hlp_acorr,     drv_separate_f64, drv_spectrogram_dev, drv_foreground_dev};
+                                      hlp_acorr,     drv_separate_f64, drv_spectrogram_dev, drv_foreground_dev, drv_single_f64_dev};
     return &table;
 }
 

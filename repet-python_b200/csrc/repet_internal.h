@@ -76,6 +76,9 @@ struct repet_entry {
     int (*spectrogram_dev)(repet_handle*, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                            const repet_params* p, float* spectrogram);
     int (*foreground_dev)(repet_handle*, const float* audio, const float* background, int64_t n, float* foreground);
+    // float64 (samples, channels) device in / device out, stream-ordered (the stateful simonline stream)
+    int (*single_f64_dev)(repet_handle*, int kind, const double* d_audio, int64_t n_samples, int n_channels,
+                          const repet_params* p, double* d_background);
 };
 
 namespace repet {

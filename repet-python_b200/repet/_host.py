@@ -96,6 +96,10 @@ SIGNATURES = {
     "repet_simonline_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_simonline_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
     "repet_simonline_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp, _c_int]),
+    "repet_simonline_open": (_c_int, [_vp, _pp, _c_int, ctypes.POINTER(_vp)]),
+    "repet_simonline_block": (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, ctypes.POINTER(_c_i64)]),
+    "repet_simonline_flush": (_c_int, [_vp, _vp, _c_i64, ctypes.POINTER(_c_i64)]),
+    "repet_simonline_close": (_c_int, [_vp]),
     "repet_separate_f64": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _pp, _vp, _vp, _vp, _vp, _c_int]),
     "repet_spectrogram_pitch": (_c_int, [_pp]),
     "repet_spectrogram_frames": (_c_int, [_pp, _c_i64]),
@@ -821,8 +825,9 @@ def original_batch_pcm16(pcm, sampling_frequency, tunables, handle=None):
     return background, periods
 
 
-class SimOnlineStream:
-    """Block-wise online REPET-SIM (repet.py:712-911) with the results of one whole-signal call.
+class SimOnlineStreamHost:
+    """Host-side reference implementation of the stream (kept for cross-checks; `SimOnlineStream` below is the
+    product path): block-wise online REPET-SIM (repet.py:712-911) with the results of one whole-signal call.
 
     `process(block)` takes the next samples (n, channels) and returns the background samples that have
     become final (every frame covering them is complete: a latency of one hop, 1024 samples at 44.1 kHz);
@@ -904,3 +909,66 @@ class SimOnlineStream:
         if self.received < (self.B - 2) * self.H + self.N:
             raise ValueError("operands could not be broadcast together (signal shorter than the buffer)")
         return self._advance(self.received, self.received)
+
+
+class SimOnlineStream:
+    """Block-wise online REPET-SIM (repet.py:712-911) on the stateful C stream (repet_simonline_open / _block /
+    _flush / _close): the last buffer_length seconds of samples live in device memory, a block costs one upload of
+    the new samples and one download of the samples that became final.
+
+    `process(block)` takes the next samples (n, channels) and returns the background samples that have become
+    final (every frame covering them is complete: a latency of one hop, 1024 samples at 44.1 kHz); `flush()`
+    returns the rest, zero-padding the last frame as the reference does.  The concatenated outputs equal
+    `repet.simonline` on the whole signal (ring-slot order of the whole stream, quirk Q6); like the reference,
+    nothing is synthesised before frame buffer_frames-1: the first ~10 s of output are zero."""
+
+    def __init__(self, sampling_frequency, number_channels, tunables, handle=None):
+        self.handle = handle or get_handle()
+        self.channels = int(number_channels)
+        self.params, _ = derive_params(sampling_frequency, dict(tunables), "simonline")
+        self.handle.ensure_window(self.params.window_length)
+        self._stream = _vp()
+        self.handle.check(self.handle.lib.repet_simonline_open(self.handle.h, ctypes.byref(self.params), self.channels,
+                                                               ctypes.byref(self._stream)))
+
+    def _call(self, fn, block):
+        hop = self.params.step_length
+        capacity = (0 if block is None else block.shape[0]) + 2 * hop if fn == "block" else self._pending + 2 * hop
+        out = np.empty((capacity, self.channels), dtype=np.float64)
+        n_out = _c_i64(0)
+        lib = self.handle.lib
+        if fn == "block":
+            rc = lib.repet_simonline_block(self._stream, _ptr(block), block.shape[0], _ptr(out), capacity, ctypes.byref(n_out))
+        else:
+            rc = lib.repet_simonline_flush(self._stream, _ptr(out), capacity, ctypes.byref(n_out))
+        self.handle.check(rc)
+        return out[: n_out.value]
+
+    _pending = 0  # samples received and not yet emitted (bounds the flush buffer)
+
+    def process(self, block):
+        block = np.ascontiguousarray(block, dtype=np.float64)
+        if block.ndim != 2 or block.shape[1] != self.channels:
+            raise ValueError("block must have shape (samples, %d)" % self.channels)
+        self.handle.ensure_window(self.params.window_length)
+        out = self._call("block", block)
+        self._pending += block.shape[0] - out.shape[0]
+        return out
+
+    def flush(self):
+        """End of stream: everything up to the last received sample."""
+        self.handle.ensure_window(self.params.window_length)
+        out = self._call("flush", None)
+        self._pending -= out.shape[0]
+        return out
+
+    def close(self):
+        if self._stream:
+            self.handle.lib.repet_simonline_close(self._stream)
+            self._stream = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -167,3 +167,28 @@ def test_sim_long_track_lists_match_the_reference(repet):
     bad = np.nonzero(digests != golden["digests"])[0]
     assert bad.size == 0, "lists differ in blocks of %d frames starting at %s" % (spec["block"], (bad * spec["block"]).tolist())
     assert np.all(np.isfinite(y))
+
+
+def test_c_stream_matches_the_host_side_stream_bit_for_bit(repet):
+    """The stateful C stream (repet_simonline_open / _block / _flush: sample history resident on the device) against
+    the host-side reference implementation of the same bookkeeping, with blocks of an awkward size: same windows, same
+    online_frame_base, so the outputs must be identical; a stream shorter than the buffer raises like the reference."""
+    x = make_golden.case_input(make_golden.DRIVER_CASES["synth_12s"])
+    x = np.concatenate([x, x[: 3 * FS + 501]])
+    pieces_c, pieces_h = [], []
+    stream_c = repet.SimOnline(FS, x.shape[1])
+    stream_h = repet._host.SimOnlineStreamHost(FS, x.shape[1], repet._tunables())
+    for k in range(0, len(x), 12345):
+        pieces_c.append(stream_c.process(x[k : k + 12345]))
+        pieces_h.append(stream_h.process(x[k : k + 12345]))
+        assert pieces_c[-1].shape == pieces_h[-1].shape
+    pieces_c.append(stream_c.flush())
+    pieces_h.append(stream_h.flush())
+    out_c, out_h = np.concatenate(pieces_c), np.concatenate(pieces_h)
+    assert out_c.shape == x.shape and np.array_equal(out_c, out_h)
+    assert stream_c.flush().shape == (0, x.shape[1])
+    stream_c.close()
+    short = repet.SimOnline(FS, 2)
+    short.process(np.full((3 * FS, 2), 0.01))
+    with pytest.raises(ValueError):
+        short.flush()
