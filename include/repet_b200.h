@@ -111,6 +111,28 @@ int repet_original_batch(repet_handle* h, const float* audio, int n_clips, int n
  * normalises by 2^15, repet.py:926-929): half the host-to-device bytes; output fp32 planar. */
 int repet_original_batch_pcm16(repet_handle* h, const int16_t* audio, int n_clips, int n_channels, int64_t n_samples,
                                const repet_params* p, float* background, int32_t* periods_host);
+/* Any driver (method 0 original, 1 extended, 2 adaptive, 3 sim, 4 simonline) over a batch of equally long clips in
+ * HOST memory, with the sample format of either side chosen by the caller:
+ *   REPET_FMT_F32_PLANAR  [n_clips][n_channels][n_samples] fp32
+ *   REPET_FMT_PCM16       [n_clips][n_samples][n_channels] int16, WAV order: what scipy.io.wavfile.read hands
+ *                         repet.wavread before it normalises by 2^15 (repet.py:926-929), and what an int16 WAVE
+ *                         writer stores after the separation (repet.wavwrite, repet.py:934-946).  Input is
+ *                         normalised on the device; output is round(y * 2^15) saturated to int16 (LOSSY: adds up to
+ *                         2^-16 of absolute error on top of the fp32 path's).
+ * PCM16 on both sides moves 2 + 2 bytes per sample over the host link instead of 4 + 4.
+ * ints_host: optional, [n_clips][repet_ints_per_clip(method, p, n_samples)]. */
+#define REPET_FMT_F32_PLANAR 0
+#define REPET_FMT_PCM16 1
+int repet_separate_batch(repet_handle* h, int method, const void* audio, int in_format, int n_clips, int n_channels,
+                         int64_t n_samples, const repet_params* p, void* background, int out_format, int32_t* ints_host);
+int64_t repet_ints_per_clip(int method, const repet_params* p, int64_t n_samples);
+/* Page-locked host memory for the host-buffer entry points (portable across the GPUs of the process): allocate
+ * it, or pin an existing allocation in place (e.g. a NumPy array) for the duration of the calls. */
+int repet_host_alloc(void** out, uint64_t bytes);
+int repet_host_free(void* ptr);
+int repet_host_register(void* ptr, uint64_t bytes);
+int repet_host_unregister(void* ptr);
+int repet_device_count(void);
 /* The reference's exact calling convention for one clip: float64 (n_samples, n_channels)
  * in and out, host pointers (repet.py:73-77). */
 int repet_original_f64(repet_handle* h, const double* audio, int64_t n_samples, int n_channels,

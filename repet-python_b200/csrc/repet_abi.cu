@@ -261,7 +261,8 @@ const char* repet_kernel_name(int id) { return (id >= 0 && id < REPET_NUM_KERNEL
                              const repet_params* p, float* background, int32_t* ints_host) {                           \
         const repet_entry* e = entry_for(h, p);                                                                        \
         if (!e) return h ? (p ? REPET_E_UNSUPPORTED : REPET_E_INVALID_ARG) : REPET_E_INVALID_ARG;                      \
-        return e->batch_host(h, KIND, audio, 0, n_clips, n_channels, n_samples, p, background, ints_host);             \
+        return e->batch_host(h, KIND, audio, REPET_FMT_F32_PLANAR, n_clips, n_channels, n_samples, p, background,     \
+                             REPET_FMT_F32_PLANAR, ints_host);                                                         \
     }
 
 REPET_DRIVER(original, KIND_ORIGINAL)
@@ -486,7 +487,71 @@ int repet_original_batch_pcm16(repet_handle* h, const int16_t* audio, int n_clip
                                const repet_params* p, float* background, int32_t* periods_host) {
     const repet_entry* e = entry_for(h, p);
     if (!e) return h ? (p ? REPET_E_UNSUPPORTED : REPET_E_INVALID_ARG) : REPET_E_INVALID_ARG;
-    return e->batch_host(h, KIND_ORIGINAL, audio, 1, n_clips, n_channels, n_samples, p, background, periods_host);
+    return e->batch_host(h, KIND_ORIGINAL, audio, REPET_FMT_PCM16, n_clips, n_channels, n_samples, p, background,
+                         REPET_FMT_F32_PLANAR, periods_host);
+}
+
+// any driver, any of the two sample formats on either side (repet.py:914-946 either side of the separation)
+int repet_separate_batch(repet_handle* h, int method, const void* audio, int in_format, int n_clips, int n_channels,
+                         int64_t n_samples, const repet_params* p, void* background, int out_format, int32_t* ints_host) {
+    const repet_entry* e = entry_for(h, p);
+    if (!e) return h ? (p ? REPET_E_UNSUPPORTED : REPET_E_INVALID_ARG) : REPET_E_INVALID_ARG;
+    if (method < KIND_ORIGINAL || method > KIND_SIMONLINE) return fail(h, REPET_E_INVALID_ARG, "unknown method");
+    return e->batch_host(h, method, audio, in_format, n_clips, n_channels, n_samples, p, background, out_format, ints_host);
+}
+
+// integer outputs per clip of a driver (the size of `ints_host` per clip for repet_separate_batch)
+int64_t repet_ints_per_clip(int method, const repet_params* p, int64_t n_samples) {
+    if (!p || p->step_length <= 0) return 0;
+    const int64_t T = (n_samples + p->step_length - 1) / p->step_length + 1;
+    switch (method) {
+        case KIND_ORIGINAL: return 1;
+        case KIND_EXTENDED: return repet_extended_segments(p, n_samples);
+        case KIND_ADAPTIVE: return T;
+        case KIND_SIM: return T * ((int64_t)p->similarity_number + 1);
+        case KIND_SIMONLINE: return (int64_t)repet_simonline_frames(p, n_samples) * ((int64_t)p->similarity_number + 1);
+    }
+    return 0;
+}
+
+// page-locked host memory for the host-buffer entry points (pageable buffers are staged by the driver at a
+// fraction of the link rate)
+int repet_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return REPET_E_INVALID_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? REPET_E_OOM : REPET_E_CUDA;
+    }
+    return REPET_OK;
+}
+int repet_host_free(void* ptr) {
+    if (!ptr) return REPET_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? REPET_OK : REPET_E_CUDA;
+}
+int repet_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr) return REPET_E_INVALID_ARG;
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return REPET_E_CUDA;
+    }
+    return REPET_OK;
+}
+int repet_host_unregister(void* ptr) {
+    if (!ptr) return REPET_OK;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    return e == cudaSuccess ? REPET_OK : REPET_E_CUDA;
+}
+int repet_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 // number of 10 s segments of repet.extended (repet.py:270-283)

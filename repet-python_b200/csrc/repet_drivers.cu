@@ -337,8 +337,9 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         CU(cudaMemsetAsync(cnt, 0, (size_t)g * T * sizeof(int32_t), st));
         if (online) {
             Timed timed(h, REPET_K_TOPK);
-            launch_online_select(st, An64, g, T, plan.buffer_frames, plan.p.online_frame_base,
-                                 plan.p.similarity_threshold, plan.distance, plan.number, idx, cnt);
+            if (launch_online_select(st, An64, g, T, plan.buffer_frames, plan.p.online_frame_base,
+                                     plan.p.similarity_threshold, plan.distance, plan.number, idx, cnt))
+                return fail(h, REPET_E_UNSUPPORTED, "buffer_length too long for the online selection kernel on this device");
         } else {
             {
                 Timed timed(h, REPET_K_SIMGEMM);
@@ -528,74 +529,95 @@ int batch_dev(repet_handle* h, int kind, const float* audio, int n_clips, int nc
     return REPET_OK;
 }
 
-// `pcm16`: the input is int16 PCM in WAV order [clip][sample][channel] (2 bytes per sample over PCIe
-// instead of 4); it is normalised by 2^15 as repet.wavread does (repet.py:929) and made planar on the
-// device.
-int batch_host(repet_handle* h, int kind, const void* audio_any, bool pcm16, int n_clips, int nch, int64_t S,
-               const repet_params* p, float* background, int32_t* ints_host) {
-    const float* audio = static_cast<const float*>(audio_any);
-    const int16_t* audio_pcm = static_cast<const int16_t*>(audio_any);
+// Host buffers in, host buffers out: copies chunked and overlapped with the compute on three streams.
+// Formats (include/repet_b200.h): REPET_FMT_F32_PLANAR [clip][channel][sample] fp32, or REPET_FMT_PCM16, int16 PCM
+// in WAV order [clip][sample][channel] (2 bytes per sample over PCIe instead of 4).  PCM input is normalised by
+// 2^15 as repet.wavread does (repet.py:929) and made planar on the device; PCM output is round(y * 2^15)
+// saturated to int16, interleaved on the device.
+int batch_host(repet_handle* h, int kind, const void* audio_any, int in_fmt, int n_clips, int nch, int64_t S,
+               const repet_params* p, void* background_any, int out_fmt, int32_t* ints_host) {
     int rc = check_common(h, p, nch);
     if (rc) return rc;
-    if (!audio || !background || n_clips < 0 || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    if (!audio_any || !background_any || n_clips < 0 || S < 0) return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    if ((in_fmt != REPET_FMT_F32_PLANAR && in_fmt != REPET_FMT_PCM16) ||
+        (out_fmt != REPET_FMT_F32_PLANAR && out_fmt != REPET_FMT_PCM16))
+        return fail(h, REPET_E_INVALID_ARG, "unknown sample format");
     if (n_clips == 0) return REPET_OK;
     CU(cudaSetDevice(h->device));
+    const bool pcm_in = in_fmt == REPET_FMT_PCM16, pcm_out = out_fmt == REPET_FMT_PCM16;
+    const unsigned char* audio = static_cast<const unsigned char*>(audio_any);
+    unsigned char* background = static_cast<unsigned char*>(background_any);
     const size_t clip_elems = (size_t)nch * (size_t)S;
     const size_t clip_bytes = clip_elems * sizeof(float);
-    // copy granularity: about copy_chunk_mb per slot, two slots in flight in each direction.  Small slots shorten
-    // the fill and drain of the H2D -> compute -> D2H pipeline (the first upload and the last download overlap
-    // nothing); the kernels have ~10x headroom over PCIe, so their efficiency on small chunks does not matter
+    const size_t in_clip_bytes = clip_elems * (pcm_in ? sizeof(int16_t) : sizeof(float));
+    const size_t out_clip_bytes = clip_elems * (pcm_out ? sizeof(int16_t) : sizeof(float));
+    // copy granularity: about copy_chunk_mb of fp32 samples per slot, two slots in flight in each direction.  Small
+    // slots shorten the fill and drain of the H2D -> compute -> D2H pipeline (the first upload and the last download
+    // overlap nothing); the kernels have ~10x headroom over PCIe, so their efficiency on small chunks does not matter
     const size_t slot_target = (size_t)std::max(8, g_tuning.copy_chunk_mb) << 20;
     int Gc = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_clips, slot_target / std::max<size_t>(1, clip_bytes)));
     Plan plan;
     if ((rc = make_plan(h, kind, p, nch, S, Gc, &plan))) return rc;
     const int Gw = std::min(Gc, chunk_clips(h, plan, Gc));
-    const size_t slot_bytes = align_up((size_t)Gc * clip_bytes);
+    const size_t in_slot_bytes = align_up((size_t)Gc * in_clip_bytes), out_slot_bytes = align_up((size_t)Gc * out_clip_bytes);
+    const size_t f32_bytes = align_up((size_t)Gc * clip_bytes);
     const size_t ints_bytes = align_up((size_t)n_clips * plan.ints_per_clip * sizeof(int32_t));
     const size_t ws_bytes = (size_t)Gw * plan.bytes_per_clip;
-    const size_t pcm_bytes = pcm16 ? slot_bytes : 0;  // one fp32 conversion target (the PCM slots are half size)
-    if ((rc = ensure_arena(h, ints_bytes + 4 * slot_bytes + pcm_bytes + ws_bytes))) return rc;
-    int32_t* ints = reinterpret_cast<int32_t*>(h->arena);
-    float* in_slot[2] = {reinterpret_cast<float*>(h->arena + ints_bytes),
-                         reinterpret_cast<float*>(h->arena + ints_bytes + slot_bytes)};
-    float* out_slot[2] = {reinterpret_cast<float*>(h->arena + ints_bytes + 2 * slot_bytes),
-                          reinterpret_cast<float*>(h->arena + ints_bytes + 3 * slot_bytes)};
-    float* converted = reinterpret_cast<float*>(h->arena + ints_bytes + 4 * slot_bytes);
-    unsigned char* ws = h->arena + ints_bytes + 4 * slot_bytes + pcm_bytes;
+    if ((rc = ensure_arena(h, ints_bytes + 2 * in_slot_bytes + 2 * out_slot_bytes + (pcm_in ? f32_bytes : 0) +
+                                  (pcm_out ? f32_bytes : 0) + ws_bytes)))
+        return rc;
+    Bump bump(h->arena);
+    int32_t* ints = reinterpret_cast<int32_t*>(bump.take<unsigned char>(ints_bytes));
+    unsigned char* in_slot[2] = {bump.take<unsigned char>(in_slot_bytes), bump.take<unsigned char>(in_slot_bytes)};
+    unsigned char* out_slot[2] = {bump.take<unsigned char>(out_slot_bytes), bump.take<unsigned char>(out_slot_bytes)};
+    float* in32 = pcm_in ? reinterpret_cast<float*>(bump.take<unsigned char>(f32_bytes)) : nullptr;
+    float* out32 = pcm_out ? reinterpret_cast<float*>(bump.take<unsigned char>(f32_bytes)) : nullptr;
+    unsigned char* ws = h->arena + bump.off;
     CU(cudaStreamSynchronize(h->stream));  // the arena must be idle before the copy streams touch it
-    int n_chunks = 0;
-    for (int first = 0; first < n_clips; first += Gc, ++n_chunks) {
-        const int s = n_chunks & 1;
-        const int g = std::min(Gc, n_clips - first);
-        if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_compute[s], 0));  // slot's input consumed
-        if (pcm16)
-            CU(cudaMemcpyAsync(in_slot[s], audio_pcm + (size_t)first * clip_elems, (size_t)g * clip_elems * sizeof(int16_t),
+    auto pipeline = [&]() -> int {
+        int n_chunks = 0;
+        for (int first = 0; first < n_clips; first += Gc, ++n_chunks) {
+            const int s = n_chunks & 1;
+            const int g = std::min(Gc, n_clips - first);
+            if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_compute[s], 0));  // slot's input consumed
+            CU(cudaMemcpyAsync(in_slot[s], audio + (size_t)first * in_clip_bytes, (size_t)g * in_clip_bytes,
                                cudaMemcpyHostToDevice, h->h2d_stream));
-        else
-            CU(cudaMemcpyAsync(in_slot[s], audio + (size_t)first * clip_elems, (size_t)g * clip_bytes,
-                               cudaMemcpyHostToDevice, h->h2d_stream));
-        CU(cudaEventRecord(h->ev_h2d[s], h->h2d_stream));
-        CU(cudaStreamWaitEvent(h->stream, h->ev_h2d[s], 0));
-        if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_d2h[s], 0));  // slot's output drained
-        const float* chunk_in = in_slot[s];
-        if (pcm16) {
-            Timed timed(h, REPET_K_CONVERT);
-            launch_pcm16_to_planar(h->stream, reinterpret_cast<const int16_t*>(in_slot[s]), g, S, nch, converted);
-            chunk_in = converted;
+            CU(cudaEventRecord(h->ev_h2d[s], h->h2d_stream));
+            CU(cudaStreamWaitEvent(h->stream, h->ev_h2d[s], 0));
+            if (n_chunks >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_d2h[s], 0));  // slot's output drained
+            const float* chunk_in = reinterpret_cast<const float*>(in_slot[s]);
+            if (pcm_in) {
+                Timed timed(h, REPET_K_CONVERT);
+                launch_pcm16_to_planar(h->stream, reinterpret_cast<const int16_t*>(in_slot[s]), g, S, nch, in32);
+                chunk_in = in32;
+            }
+            float* chunk_out = pcm_out ? out32 : reinterpret_cast<float*>(out_slot[s]);
+            int rc2 = run_plan(h, plan, chunk_in, g, chunk_out, ints + (size_t)first * plan.ints_per_clip, ws, ws_bytes);
+            if (rc2) return rc2;
+            if (pcm_out) {
+                Timed timed(h, REPET_K_CONVERT);
+                launch_planar_to_pcm16(h->stream, out32, g, S, nch, reinterpret_cast<int16_t*>(out_slot[s]));
+            }
+            CU(cudaEventRecord(h->ev_compute[s], h->stream));
+            CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute[s], 0));
+            CU(cudaMemcpyAsync(background + (size_t)first * out_clip_bytes, out_slot[s], (size_t)g * out_clip_bytes,
+                               cudaMemcpyDeviceToHost, h->d2h_stream));
+            CU(cudaEventRecord(h->ev_d2h[s], h->d2h_stream));
         }
-        rc = run_plan(h, plan, chunk_in, g, out_slot[s], ints + (size_t)first * plan.ints_per_clip, ws, ws_bytes);
-        if (rc) return rc;
-        CU(cudaEventRecord(h->ev_compute[s], h->stream));
-        CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_compute[s], 0));
-        CU(cudaMemcpyAsync(background + (size_t)first * clip_elems, out_slot[s], (size_t)g * clip_bytes,
-                           cudaMemcpyDeviceToHost, h->d2h_stream));
-        CU(cudaEventRecord(h->ev_d2h[s], h->d2h_stream));
-    }
-    if (ints_host)
-        CU(cudaMemcpyAsync(ints_host, ints, (size_t)n_clips * plan.ints_per_clip * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                           h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaStreamSynchronize(h->d2h_stream));
+        if (ints_host)
+            CU(cudaMemcpyAsync(ints_host, ints, (size_t)n_clips * plan.ints_per_clip * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, h->stream));
+        return REPET_OK;
+    };
+    rc = pipeline();
+    // also on the error path: copies from / into the caller's buffers may still be in flight, and the caller is
+    // free to release them as soon as this returns
+    const cudaError_t e1 = cudaStreamSynchronize(h->h2d_stream), e2 = cudaStreamSynchronize(h->stream),
+                      e3 = cudaStreamSynchronize(h->d2h_stream);
+    if (rc) return rc;
+    CU(e1);
+    CU(e2);
+    CU(e3);
     return REPET_OK;
 }
 
@@ -734,9 +756,9 @@ int drv_batch_dev(repet_handle* h, int kind, const float* audio, int n_clips, in
                   const repet_params* p, float* background, int32_t* ints_dev, int32_t* ints_host) {
     return batch_dev(h, kind, audio, n_clips, n_channels, n_samples, p, background, ints_dev, ints_host, nullptr);
 }
-int drv_batch_host(repet_handle* h, int kind, const void* audio, int pcm16, int n_clips, int n_channels,
-                   int64_t n_samples, const repet_params* p, float* background, int32_t* ints) {
-    return batch_host(h, kind, audio, pcm16 != 0, n_clips, n_channels, n_samples, p, background, ints);
+int drv_batch_host(repet_handle* h, int kind, const void* audio, int in_format, int n_clips, int n_channels,
+                   int64_t n_samples, const repet_params* p, void* background, int out_format, int32_t* ints) {
+    return batch_host(h, kind, audio, in_format, n_clips, n_channels, n_samples, p, background, out_format, ints);
 }
 int drv_single_f64(repet_handle* h, int kind, const double* audio, int64_t n_samples, int n_channels,
                    const repet_params* p, double* background, int32_t* ints, int64_t ints_capacity) {

@@ -9,7 +9,7 @@
 namespace repet {
 
 int drv_batch_dev(repet_handle*, int, const float*, int, int, int64_t, const repet_params*, float*, int32_t*, int32_t*);
-int drv_batch_host(repet_handle*, int, const void*, int, int, int, int64_t, const repet_params*, float*, int32_t*);
+int drv_batch_host(repet_handle*, int, const void*, int, int, int, int64_t, const repet_params*, void*, int, int32_t*);
 int drv_single_f64(repet_handle*, int, const double*, int64_t, int, const repet_params*, double*, int32_t*, int64_t);
 int drv_separate_f64(repet_handle*, int, const double*, int64_t, int, const repet_params*, double*, double*, float*,
                      int32_t*, int64_t);

@@ -52,8 +52,8 @@ struct repet_entry {
     // drivers: kind = 0 original, 1 extended, 2 adaptive, 3 sim, 4 simonline
     int (*batch_dev)(repet_handle*, int kind, const float* audio, int n_clips, int n_channels, int64_t n_samples,
                      const repet_params* p, float* background, int32_t* ints_dev, int32_t* ints_host);
-    int (*batch_host)(repet_handle*, int kind, const void* audio, int pcm16, int n_clips, int n_channels,
-                      int64_t n_samples, const repet_params* p, float* background, int32_t* ints);
+    int (*batch_host)(repet_handle*, int kind, const void* audio, int in_format, int n_clips, int n_channels,
+                      int64_t n_samples, const repet_params* p, void* background, int out_format, int32_t* ints);
     int (*single_f64)(repet_handle*, int kind, const double* audio, int64_t n_samples, int n_channels,
                       const repet_params* p, double* background, int32_t* ints, int64_t ints_capacity);
     // helpers

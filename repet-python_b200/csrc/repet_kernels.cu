@@ -291,11 +291,8 @@ static void go_beat(cudaStream_t st, const float* P, int n_items, int T, int t_f
                     FftTables tb, float* psd_part, int n_parts, int f_per_part) {
     int TP;
     size_t smem = beat_smem_bytes<BL>(t_len, &TP);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_beat<BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    smem_opt_in(k_beat<BL>, smem, opt_in);
     dim3 grid(n_parts, n_items * n_seg);
     k_beat<BL><<<grid, BL / 16, smem, st>>>(P, T, t_first, t_len, seg_step, n_seg, tb, psd_part, n_parts, f_per_part, TP);
 }
@@ -449,11 +446,8 @@ void launch_periods(cudaStream_t st, const float* psd_part, const float* psd_par
                     int t_len, double norm_rows, int lag_lo, int lag_hi, int out_lo, int out_hi, double* beat_out,
                     int beat_pitch, int* period, double* stats, int* cert, int L) {
     const size_t smem = (size_t)(2 * BEAT_L + 2 * (BEAT_L / 2 + 1)) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_periods, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static SmemOptIn opt_in;
+    smem_opt_in(k_periods, smem, opt_in);
     k_periods<<<n_beat_items, 256, smem, st>>>(psd_part, psd_part_im, n_parts, t_len, norm_rows, lag_lo, lag_hi, out_lo,
                                               out_hi, beat_out, beat_pitch, period, stats, cert,
                                               g_tuning.cert_rel_ppm > 0 ? 1e-6 * g_tuning.cert_rel_ppm : CERT_REL, L);
@@ -655,11 +649,8 @@ void launch_beat_blocked(cudaStream_t st, const float* P, int n_items, int T, in
     const int rows = Bk + max_lag - 1;
     const int TP = ((rows + 7) / 8) * 8 + 4;
     const size_t smem = (size_t)(2 * TF::BUF + TF::TW2) * sizeof(float2) + (size_t)8 * TP * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_beat_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    smem_opt_in(k_beat_blocked, smem, opt_in);
     dim3 grid(n_fparts, n_blocks, n_items);
     k_beat_blocked<<<grid, TF::THREADS, smem, st>>>(P, T, Bk, max_lag, tb, g_re, g_im, n_fparts, f_per_part, TP);
 }
@@ -1069,9 +1060,8 @@ k_mask_istft(const float2* __restrict__ X, Geom g, const int* __restrict__ perio
 template <int NCH, bool MASKED, int MINB>
 static void go_mask_istft(cudaStream_t st, dim3 grid, const float2* X, Geom g, const int* period, int pmax,
                           const float* model, int cutoff, float scale, FftTables tb, float* out, int blocks_per_cta) {
-    // per device, so it is not cached in a static: the call is a few hundred ns
-    cudaFuncSetAttribute(k_mask_istft<NCH, MASKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)MASK_ISTFT_SMEM);
+    static SmemOptIn opt_in;
+    smem_opt_in(k_mask_istft<NCH, MASKED, MINB>, MASK_ISTFT_SMEM, opt_in);
     k_mask_istft<NCH, MASKED, MINB><<<grid, FF::THREADS, MASK_ISTFT_SMEM, st>>>(X, g, period, pmax, model, cutoff, scale,
                                                                                   tb, out, blocks_per_cta);
 }
@@ -1351,6 +1341,23 @@ __global__ void k_pcm16_to_planar(const int16_t* __restrict__ in, long long S, i
 void launch_pcm16_to_planar(cudaStream_t st, const int16_t* in, int n_clips, long long S, int C, float* out) {
     dim3 grid((unsigned)((S + 255) / 256), n_clips);
     k_pcm16_to_planar<<<grid, 256, 0, st>>>(in, S, C, out);
+}
+
+// fp32 planar [clip][channel][sample] -> int16 PCM in WAV order [clip][sample][channel]: round(y * 2^15) to nearest
+// (ties to even), saturated -- the inverse of the normalisation above, what an int16 WAVE writer stores
+__global__ void k_planar_to_pcm16(const float* __restrict__ in, long long S, int C, int16_t* __restrict__ out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const long long clip = blockIdx.y;
+    int16_t* __restrict__ dst = out + (clip * S + s) * C;
+    for (int c = 0; c < C; ++c) {
+        const int q = __float2int_rn(in[(clip * C + c) * S + s] * 32768.0f);
+        dst[c] = (int16_t)max(-32768, min(32767, q));
+    }
+}
+void launch_planar_to_pcm16(cudaStream_t st, const float* in, int n_clips, long long S, int C, int16_t* out) {
+    dim3 grid((unsigned)((S + 255) / 256), n_clips);
+    k_planar_to_pcm16<<<grid, 256, 0, st>>>(in, S, C, out);
 }
 
 // foreground = audio - background (README.md:68), 16 bytes per thread, tail by the last threads

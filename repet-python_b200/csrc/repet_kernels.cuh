@@ -71,6 +71,25 @@ struct FftTables {
 
 enum PMode { P_NONE = 0, P_POWER = 1, P_MAGNITUDE = 2, P_MIXDOWN = 3 };  // MIXDOWN: |STFT(mean_c x)| only, no X
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what each device has been
+// given (one handle per GPU in one process).  Returns false when the device refuses the size.
+struct SmemOptIn {
+    size_t bytes[64] = {0};
+};
+template <typename F>
+inline bool smem_opt_in(F func, size_t smem, SmemOptIn& state) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (smem <= state.bytes[dev]) return true;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    state.bytes[dev] = smem;
+    return true;
+}
+
 using Tuning = ::repet_tuning;
 static Tuning& g_tuning = ::g_repet_tuning;
 
@@ -142,8 +161,9 @@ int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_i
 void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
                 int number, int* idx_out, int* cnt_out, int* overflow);
-void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
-                          int d, int number, int* idx_out, int* cnt_out);
+// returns 0, or nonzero when the device refuses the shared memory / scratch the ring needs
+int launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
+                         int d, int number, int* idx_out, int* cnt_out);
 void launch_sqmag(cudaStream_t st, const float2* X, long long n_rows, float* Vsq);
 // Vsq (squared magnitudes [item][T][nch][PPITCH]) is required when number > 32
 int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_items, int T, int nch, const int* idx,
@@ -159,6 +179,7 @@ void launch_foreground(cudaStream_t st, const float* audio, const float* backgro
 
 // layout converters for the float64 (S, C) NumPy convention of the reference API
 void launch_pcm16_to_planar(cudaStream_t st, const int16_t* in, int n_clips, long long S, int C, float* out);
+void launch_planar_to_pcm16(cudaStream_t st, const float* in, int n_clips, long long S, int C, int16_t* out);
 void launch_f64_interleaved_to_planar(cudaStream_t st, const double* in, long long S, int C, float* out);
 void launch_planar_to_f64_interleaved(cudaStream_t st, const float* in, long long S, int C, double* out);
 

@@ -212,12 +212,9 @@ void launch_frames64(cudaStream_t st, const float* audio, const double* audio64,
                      const double* window64, const double2* tw64, double* An64, float* An32, float* An32lo,
                      int round_tf32) {
     const size_t smem = (size_t)(2 * F64::BUF + F64::TW2) * sizeof(double2);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_frames64<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_frames64<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static SmemOptIn opt_in1, opt_in2;
+    smem_opt_in(k_frames64<1>, smem, opt_in1);
+    smem_opt_in(k_frames64<2>, smem, opt_in2);
     dim3 grid((g.T + F64_FRAMES - 1) / F64_FRAMES, g.n_items);
     if (nch == 2)
         k_frames64<2><<<grid, F64::THREADS, smem, st>>>(audio, audio64, g, window64, tw64, An64, An32, An32lo, round_tf32);
@@ -566,11 +563,8 @@ int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items
         if (nb < 3) return -1;  // similarity_distance too large for the shared-memory window
     }
     const size_t smem = (size_t)APITCH64 * 8 + (size_t)TOPK_CAP * 16 + 3 * (size_t)TOPK_CHUNK * 4;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static SmemOptIn opt_in;
+    smem_opt_in(k_topk, smem, opt_in);
     dim3 grid(T, n_items);
     k_topk<<<grid, TOPK_THREADS, smem, st>>>(S, An64, T, tau, thr, d, number, nb, idx_out, cnt_out, overflow);
     return 0;
@@ -598,17 +592,21 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
 
 __global__ void __launch_bounds__(512)
 k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, double thr, int d, int number,
-                int* __restrict__ idx_out, int* __restrict__ cnt_out) {
+                int* __restrict__ idx_out, int* __restrict__ cnt_out, int item0, int cta0, unsigned char* scratch,
+                size_t scratch_per_cta) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* s_tgt = reinterpret_cast<double*>(smem);          // [ONLINE_FB][TGT_PITCH]  target frames
-    double* s_sim = s_tgt + ONLINE_FB * TGT_PITCH;            // [ONLINE_FB][B]          similarity by ring slot
-    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_sim + ONLINE_FB * B);  // [ONLINE_FB][B]
+    // similarity by ring slot [ONLINE_FB][B] and keep flags [ONLINE_FB][B]: shared memory, or -- for rings too long
+    // for it (buffer_length above ~16 s at 44.1 kHz) -- this CTA's slice of a global scratch buffer (L2 resident)
+    double* s_sim = scratch ? reinterpret_cast<double*>(scratch + (size_t)blockIdx.x * scratch_per_cta)
+                            : s_tgt + ONLINE_FB * TGT_PITCH;
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_sim + ONLINE_FB * B);
     __shared__ int s_kept[ONLINE_FB];
-    const int item = blockIdx.y;
+    const int item = item0 + blockIdx.y;
     // rows are frames frame_base .. frame_base + T - 1 of the stream; the first synthesised row is the
     // one whose absolute index is B - 1
     const int row_first = max(0, B - 1 - frame_base);
-    const int j_first = blockIdx.x * ONLINE_FB + row_first;
+    const int j_first = (cta0 + blockIdx.x) * ONLINE_FB + row_first;
     const int nf = min(ONLINE_FB, T - j_first);  // target frames of this CTA
     if (nf <= 0) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
@@ -754,19 +752,42 @@ k_online_select(const double* __restrict__ An64, int T, int B, int frame_base, d
     if (t < nf) cnt_out[(size_t)item * T + j_first + t] = min(s_kept[t], number);
 }
 
-void launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
-                          int d, int number, int* idx_out, int* cnt_out) {
+int launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
+                         int d, int number, int* idx_out, int* cnt_out) {
     const int row_first = std::max(0, B - 1 - frame_base);
-    if (T <= row_first) return;
-    const size_t smem = (size_t)ONLINE_FB * TGT_PITCH * 8 + (size_t)ONLINE_FB * B * 9 + 16;
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k_online_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    if (T <= row_first) return 0;
+    const size_t tgt_bytes = (size_t)ONLINE_FB * TGT_PITCH * 8 + 16;
+    const size_t sel_bytes = ((size_t)ONLINE_FB * B * 9 + 15) / 16 * 16;
+    int dev = 0, max_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    static SmemOptIn opt_in;
     const int n_targets = T - row_first;
-    dim3 grid((n_targets + ONLINE_FB - 1) / ONLINE_FB, n_items);
-    k_online_select<<<grid, 512, smem, st>>>(An64, T, B, frame_base, thr, d, number, idx_out, cnt_out);
+    const int n_cta = (n_targets + ONLINE_FB - 1) / ONLINE_FB;
+    if (tgt_bytes + sel_bytes <= (size_t)max_optin) {
+        const size_t smem = tgt_bytes + sel_bytes;
+        if (smem > 48 * 1024 && !smem_opt_in(k_online_select, smem, opt_in)) return -1;
+        dim3 grid(n_cta, n_items);
+        k_online_select<<<grid, 512, smem, st>>>(An64, T, B, frame_base, thr, d, number, idx_out, cnt_out, 0, 0, nullptr, 0);
+        return 0;
+    }
+    // ring longer than shared memory holds: similarity rows in a stream-ordered global scratch buffer, at most
+    // 256 MB of it in flight per launch
+    if (!smem_opt_in(k_online_select, tgt_bytes, opt_in)) return -1;
+    const int per_launch = (int)std::min<size_t>((size_t)n_cta, std::max<size_t>(1, ((size_t)256 << 20) / sel_bytes));
+    unsigned char* scratch = nullptr;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)per_launch * sel_bytes, st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -2;
+    }
+    for (int item = 0; item < n_items; ++item)
+        for (int cta0 = 0; cta0 < n_cta; cta0 += per_launch) {
+            dim3 grid(std::min(per_launch, n_cta - cta0), 1);
+            k_online_select<<<grid, 512, tgt_bytes, st>>>(An64, T, B, frame_base, thr, d, number, idx_out, cnt_out, item,
+                                                          cta0, scratch, sel_bytes);
+        }
+    cudaFreeAsync(scratch, st);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1043,11 +1064,8 @@ int launch_simmodel(cudaStream_t st, const float2* X, const float* Vsq, int n_it
     const size_t smem = (size_t)((number + 3) & ~3) * 4 + (number > 32 ? (size_t)number * 256 * 4 : 0);
     if (smem > 220 * 1024) return -1;
     if (number > 32 && !Vsq) return -2;
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k_simmodel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (smem > 48 * 1024 && !smem_opt_in(k_simmodel, smem, opt_in)) return -1;
     if (T <= first_frame) return 0;
     dim3 grid(T - first_frame, n_items * nch);
     k_simmodel<<<grid, SIMMODEL_THREADS, smem, st>>>(X, Vsq, T, nch, idx, cnt, number, first_frame, model);
@@ -1124,11 +1142,8 @@ int launch_localmaxima64(cudaStream_t st, const double* data, int n, int n_colum
                          int* idx_out, int* cnt_out, double* val_out) {
     const size_t smem = (size_t)n * 9 + 16;
     if (smem > 220 * 1024) return -1;
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k_localmaxima64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (smem > 48 * 1024 && !smem_opt_in(k_localmaxima64, smem, opt_in)) return -1;
     k_localmaxima64<<<n_columns, 256, smem, st>>>(data, n, n_columns, thr, d, number, idx_out, cnt_out, val_out);
     return 0;
 }

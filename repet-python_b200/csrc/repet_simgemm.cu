@@ -331,12 +331,9 @@ int launch_gemm(cudaStream_t st, const float* hi, const float* lo, int n_items, 
     const size_t rows = (size_t)n_items * T;
     if (!make_map(&map_a, hi, rows, BM) || !make_map(&map_b, hi, rows, BN)) return -1;
     if (!make_map(&map_a_lo, SPLIT3 ? lo : hi, rows, BM) || !make_map(&map_b_lo, SPLIT3 ? lo : hi, rows, BN)) return -1;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_simgemm<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) !=
-            cudaSuccess)
-            return -2;
-        configured = true;
+    static SmemOptIn opt_in;
+    {
+        if (!smem_opt_in(k_simgemm<BN, SPLIT3>, (size_t)Cfg::SMEM, opt_in)) return -2;
     }
     const int mt = (T + BM - 1) / BM, nt = (T + BN - 1) / BN;
     const int tiles_total = n_items * (BM == BN ? nt * (nt + 1) / 2 : mt * nt);

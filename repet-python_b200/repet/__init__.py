@@ -86,7 +86,7 @@ def original(audio_signal, sampling_frequency):
     return _host.original_f64(audio_signal, sampling_frequency, _tunables())
 
 
-def original_batch(audio_signals, sampling_frequency):
+def original_batch(audio_signals, sampling_frequency, devices=None):
     """
     The original REPET over a batch of equally long clips in one call.
 
@@ -100,11 +100,43 @@ def original_batch(audio_signals, sampling_frequency):
     A list / tuple of (number_channels, number_samples_i) arrays of DIFFERENT lengths is accepted too: the clips
     are grouped by shape (never padded: a clip's period range depends on its length) and the outputs come back as
     a list of backgrounds and an int32 array of periods, in input order.
+
+    `devices` (e.g. range(8)) shards the batch by clip over several GPUs inside this process: one handle and one
+    host thread per GPU, no collective (clips are independent).
     """
     if isinstance(audio_signals, (list, tuple)):
         backgrounds, periods = _host.driver_batch_ragged("original", audio_signals, sampling_frequency, _tunables())
         return backgrounds, np.array([int(p[0]) for p in periods], dtype=np.int32)
+    if devices is not None:
+        background, periods = _host.separate_batch("original", audio_signals, sampling_frequency, _tunables(), devices=devices)
+        return background, periods[:, 0]
     return _host.original_batch(audio_signals, sampling_frequency, _tunables())
+
+
+def separate_batch(audio_signals, sampling_frequency, method="original", in_format="f32", out_format="f32", out=None,
+                   devices=None):
+    """
+    Any of the five methods over a batch of equally long clips, with the sample format of either side chosen by
+    the caller (the steps either side of the separation in the reference's usage, repet.py:914-946):
+
+        in_format  "f32": (number_clips, number_channels, number_samples) float32, planar
+                   "pcm16": (number_clips, number_samples, number_channels) int16 as scipy.io.wavfile.read returns
+                            it; normalised by 2^15 on the device, as repet.wavread does (repet.py:929)
+        out_format "f32" or "pcm16" (round(y * 2^15) saturated to int16: lossy, for int16 WAVE writers)
+        devices    optional GPU indices: clip-sharded over them inside this process (one thread per GPU)
+
+    Outputs: background_signals in `out_format`; integers int32 (number_clips, per clip: 1 period | segment periods |
+    frame periods | [counts][indices] lists).  `repet.pinned_empty` allocates page-locked arrays for `audio_signals`
+    and `out`, which the copies need to run at the full rate of the host link.
+    """
+    return _host.separate_batch(method, audio_signals, sampling_frequency, _tunables(), in_format=in_format,
+                                out_format=out_format, out=out, devices=devices)
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """An uninitialised NumPy array on page-locked host memory; keep the returned holder alive while the array is
+    in use: `holder = repet.pinned_empty(shape); x = holder.array`."""
+    return _host.PinnedArray(shape, dtype)
 
 
 def original_batch_pcm16(pcm_signals, sampling_frequency):

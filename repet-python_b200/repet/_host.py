@@ -73,6 +73,13 @@ SIGNATURES = {
     "repet_original_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
     "repet_original_batch": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
     "repet_original_batch_pcm16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp]),
+    "repet_separate_batch": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_i64, _pp, _vp, _c_int, _vp]),
+    "repet_ints_per_clip": (_c_i64, [_c_int, _pp, _c_i64]),
+    "repet_host_alloc": (_c_int, [ctypes.POINTER(_vp), _c_u64]),
+    "repet_host_free": (_c_int, [_vp]),
+    "repet_host_register": (_c_int, [_vp, _c_u64]),
+    "repet_host_unregister": (_c_int, [_vp]),
+    "repet_device_count": (_c_int, []),
     "repet_original_f64": (_c_int, [_vp, _vp, _c_i64, _c_int, _pp, _vp, _vp]),
     "repet_extended_segments": (_c_int, [_pp, _c_i64]),
     "repet_extended_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp, _vp, _vp]),
@@ -258,14 +265,21 @@ _PARAM_CACHE = {}
 
 def derive_params(sampling_frequency, tunables, driver="original"):
     """Cached front end of _derive_params (the derivation is pure; batch callers hit it every step)."""
-    key = (float(sampling_frequency), driver, tuple((k, tuple(v) if isinstance(v, (list, tuple)) else v)
-                                                    for k, v in sorted(tunables.items())))
-    hit = _PARAM_CACHE.get(key)
+    try:
+        # array-likes (lists, tuples, NumPy arrays -- the reference takes np.array(period_range)) become tuples,
+        # NumPy scalars plain numbers
+        key = (float(sampling_frequency), driver,
+               tuple((k, tuple(np.ravel(v).tolist()) if np.ndim(v) else (v.item() if isinstance(v, np.generic) else v))
+                     for k, v in sorted(tunables.items())))
+        hit = _PARAM_CACHE.get(key)
+    except TypeError:  # an unhashable tunable: derive uncached
+        key, hit = None, None
     if hit is None:
         hit = _derive_params(sampling_frequency, tunables, driver)
-        if len(_PARAM_CACHE) > 64:
-            _PARAM_CACHE.clear()
-        _PARAM_CACHE[key] = hit
+        if key is not None:
+            if len(_PARAM_CACHE) > 64:
+                _PARAM_CACHE.clear()
+            _PARAM_CACHE[key] = hit
     params = RepetParams()
     ctypes.memmove(ctypes.byref(params), ctypes.byref(hit[0]), ctypes.sizeof(RepetParams))
     return params, hit[1]
@@ -402,9 +416,15 @@ def istft_half(spectrum, window_function, step_length, handle=None):
     """Inverse of stft_half: complex (C, T, F) -> float32 (C, (T-1)*H)."""
     handle = handle or get_handle()
     window_length = len(window_function)
+    if step_length * 2 != window_length:
+        raise NotImplementedError("step_length must be window_length/2")
+    # the library's instantiation follows the window set last: select it here (repet_istft itself only uses the
+    # window's length and COLA gain)
+    handle.set_window(window_function)
     half = window_length // 2
     number_channels, number_times, number_frequencies = spectrum.shape
-    assert number_frequencies == half + 1
+    if number_frequencies != half + 1:
+        raise ValueError("spectrum must hold window_length/2 + 1 bins")
     packed = np.empty((number_times, number_channels, half, 2), dtype=np.float32)
     packed[..., 0] = np.transpose(spectrum[:, :, :half].real, (1, 0, 2))
     packed[..., 1] = np.transpose(spectrum[:, :, :half].imag, (1, 0, 2))
@@ -601,6 +621,121 @@ def driver_batch(driver, audio, sampling_frequency, tunables, handle=None):
         )
     )
     return background, ints
+
+
+FORMATS = {"f32": 0, "pcm16": 1}  # REPET_FMT_F32_PLANAR, REPET_FMT_PCM16
+
+
+class PinnedArray:
+    """A NumPy array on page-locked host memory (repet_host_alloc): host-buffer batch calls copy from / into it at
+    the full rate of the host link, pageable arrays are staged by the driver at a fraction of it.  `.array` is
+    the ndarray; the memory is released when the object is (keep it alive while views of the array are in use)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        dtype = np.dtype(dtype)
+        number_bytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        pointer = _vp()
+        rc = self.lib.repet_host_alloc(ctypes.byref(pointer), max(1, number_bytes))
+        if rc != REPET_OK:
+            raise MemoryError("repet_host_alloc(%d bytes) failed with status %d" % (number_bytes, rc))
+        self.pointer = pointer
+        buffer = (ctypes.c_char * max(1, number_bytes)).from_address(pointer.value)
+        self.array = np.frombuffer(buffer, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+    def close(self):
+        if getattr(self, "pointer", None):
+            self.array = None
+            self.lib.repet_host_free(self.pointer)
+            self.pointer = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count():
+    return int(load_library().repet_device_count())
+
+
+def shard_bounds(number_clips, number_shards):
+    """Contiguous balanced split of `number_clips` over `number_shards`: list of (first, stop).  The same split as
+    repet_shard.shard_range (one process per GPU); here one host thread per GPU."""
+    base, extra = divmod(int(number_clips), int(number_shards))
+    bounds, first = [], 0
+    for r in range(int(number_shards)):
+        stop = first + base + (1 if r < extra else 0)
+        bounds.append((first, stop))
+        first = stop
+    return bounds
+
+
+def separate_batch(driver, audio, sampling_frequency, tunables, handle=None, in_format="f32", out_format="f32",
+                   out=None, devices=None):
+    """Any driver over a batch of equally long clips in host memory (repet_separate_batch).
+
+    audio: (B, C, S) float32 planar (`in_format="f32"`) or (B, S, C) int16 PCM in WAV order (`"pcm16"`: what
+    scipy.io.wavfile.read returns, normalised by 2^15 on the device as repet.wavread does, repet.py:929).
+    Output: background in `out_format` -- "f32" (B, C, S) float32, or "pcm16" (B, S, C) int16 = round(y * 2^15)
+    saturated (lossy) -- and the integer outputs (B, ints_per_clip) int32.
+
+    `devices`: a sequence of GPU indices shards the batch by clip over them inside this process, one handle and
+    one host thread per GPU over the same C entry point (clips are independent: no collective)."""
+    if driver not in METHODS:
+        raise ValueError("unknown driver %r" % driver)
+    in_code, out_code = FORMATS[in_format], FORMATS[out_format]
+    audio = np.ascontiguousarray(audio, dtype=np.int16 if in_code else np.float32)
+    if audio.ndim != 3:
+        raise ValueError("audio must have shape (clips, channels, samples) [f32] or (clips, samples, channels) [pcm16]")
+    if in_code:
+        number_clips, number_samples, number_channels = audio.shape
+    else:
+        number_clips, number_channels, number_samples = audio.shape
+    params, _ = derive_params(sampling_frequency, tunables, driver)
+    lib = load_library()
+    per_clip = int(lib.repet_ints_per_clip(METHODS[driver], ctypes.byref(params), number_samples))
+    out_shape = (number_clips, number_samples, number_channels) if out_code else (number_clips, number_channels, number_samples)
+    out_dtype = np.int16 if out_code else np.float32
+    if out is None:
+        out = np.empty(out_shape, dtype=out_dtype)
+    elif out.shape != out_shape or out.dtype != out_dtype or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous %s array of shape %s" % (np.dtype(out_dtype).name, out_shape))
+    ints = np.zeros((number_clips, max(1, per_clip)), dtype=np.int32)
+
+    def run(h, first, stop):
+        if stop <= first:
+            return
+        h.ensure_window(params.window_length)
+        h.check(lib.repet_separate_batch(
+            h.h, METHODS[driver], _ptr(audio[first:stop]), in_code, stop - first, number_channels, number_samples,
+            ctypes.byref(params), _ptr(out[first:stop]), out_code, _ptr(ints[first:stop])))
+
+    if devices is None:
+        run(handle or get_handle(), 0, number_clips)
+        return out, ints
+    devices = [int(d) for d in devices]
+    if not devices:
+        raise ValueError("devices must name at least one GPU")
+    handles = [get_handle(d) for d in devices]  # created on this thread: one handle per GPU
+    errors = []
+
+    def worker(h, first, stop):
+        try:
+            run(h, first, stop)
+        except BaseException as exc:  # re-raised on the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(h, lo, hi))
+               for h, (lo, hi) in zip(handles, shard_bounds(number_clips, len(devices)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out, ints
 
 
 def ragged_groups(shapes):

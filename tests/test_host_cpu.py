@@ -194,3 +194,33 @@ def test_ragged_batches_are_grouped_by_shape_not_padded():
     assert repet._host.ragged_groups([]) == []
     with pytest.raises(ValueError):
         repet._host.ragged_groups([(2, 1000, 1)])
+
+
+def test_shard_bounds_cover_the_batch_in_order():
+    """In-process multi-GPU sharding (repet.separate_batch(devices=...)): contiguous, balanced, same split as the
+    one-process-per-GPU repet_shard.shard_range."""
+    import repet_shard
+    from repet import _host
+
+    for n in (0, 1, 7, 8, 512, 4097):
+        for g in (1, 2, 3, 8):
+            bounds = _host.shard_bounds(n, g)
+            assert len(bounds) == g and bounds[0][0] == 0 and bounds[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+            sizes = [hi - lo for lo, hi in bounds]
+            assert max(sizes) - min(sizes) <= 1
+            assert [tuple(repet_shard.shard_range(n, r, g)) for r in range(g)] == bounds
+
+
+def test_param_cache_accepts_array_tunables():
+    from repet import _host
+
+    base = dict(cutoff_frequency=100, period_range=[1, 10], segment_length=10, segment_step=5, filter_order=5,
+                similarity_threshold=0, similarity_distance=1, similarity_number=100, buffer_length=10)
+    p_list, _ = _host.derive_params(44100, base)
+    arr = dict(base, period_range=np.array([1, 10]), filter_order=np.int64(5))
+    p_arr, _ = _host.derive_params(44100, arr)
+    assert (p_arr.period_lo, p_arr.period_hi, p_arr.filter_order) == (p_list.period_lo, p_list.period_hi, p_list.filter_order)
+    odd = dict(base, period_range=[[1], [10]])  # nested: still derivable, cached or not
+    p_odd, _ = _host.derive_params(44100, odd)
+    assert (p_odd.period_lo, p_odd.period_hi) == (p_list.period_lo, p_list.period_hi)
