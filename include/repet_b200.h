@@ -277,6 +277,25 @@ int repet_simmask(repet_handle* h, const float* magnitude, int n_frames, const i
  * unbiased autocorrelation of every column, float64 [n_rows][n_columns]. */
 int repet_acorr(repet_handle* h, const float* data, int n_rows, int n_columns, double* autocorrelation);
 
+/* ---- general-size float64 helpers ----------------------------------------------------------
+ * The reference's private helpers take ANY window, step and matrix size (its README calls _stft directly,
+ * README.md:79-81); these entry points do too, in float64 throughout (power-of-two transforms by radix-2 passes,
+ * any other length by Bluestein's algorithm).  HOST pointers. */
+/* number of frames of _stft (repet.py:1018-1028) for any window length and step */
+int repet_stft_frames(int64_t n_samples, int window_length, int step_length);
+/* _stft (repet.py:1001-1060): signal[n_samples], window[window_length] -> spectrum, the reference's own layout:
+ * (window_length, n_frames) C-order complex128, i.e. double[window_length][n_frames][2], all bins. */
+int repet_stft_f64(repet_handle* h, const double* signal, int64_t n_samples, const double* window, int window_length,
+                   int step_length, double* spectrum, int32_t* n_frames_out);
+/* _istft (repet.py:1063-1105): spectrum as above -> signal[n_frames*step - (window_length - step)]
+ * (real part of the inverse transforms, overlap-add, trim, divide by sum(window[0:N:step])). */
+int repet_istft_f64(repet_handle* h, const double* spectrum, int window_length, int n_frames, const double* window,
+                    int step_length, double* signal, int64_t* n_samples_out);
+/* _acorr (repet.py:1108-1139), any n_rows: data[n_rows][n_columns] float64 row-major -> same shape. */
+int repet_acorr_f64(repet_handle* h, const double* data, int n_rows, int n_columns, double* autocorrelation);
+/* _beatspectrum (repet.py:1142-1158), any size: spectrogram[n_frequencies][n_times] float64 -> beat[n_times]. */
+int repet_beatspectrum_f64(repet_handle* h, const double* spectrogram, int n_frequencies, int n_times, double* beat);
+
 #ifdef __cplusplus
 }
 #endif

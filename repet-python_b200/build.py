@@ -19,7 +19,7 @@ LIB = os.path.join(LIB_DIR, "librepet_b200.so")
 PER_WINDOW_SOURCES = ["repet_kernels.cu", "repet_sim.cu", "repet_simgemm.cu", "repet_drivers.cu", "repet_helpers.cu"]
 WINDOW_LENGTHS = [512, 1024, 2048]
 # compiled once: handle lifetime and the extern "C" dispatch
-COMMON_SOURCES = ["repet_abi.cu"]
+COMMON_SOURCES = ["repet_abi.cu", "repet_generic.cu"]
 SOURCES = PER_WINDOW_SOURCES + COMMON_SOURCES
 HEADERS = ["repet_kernels.cuh", "fft_core.cuh", "median_networks.cuh", "median_networks_large.cuh", "repet_internal.h", os.path.join("..", "..", "include", "repet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

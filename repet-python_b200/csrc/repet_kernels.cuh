@@ -24,6 +24,7 @@ struct repet_tuning {
     int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
     int copy_chunk_mb = 128; // host-buffer entry points: megabytes per copy slot (pipeline granularity)
     int sim_frames64 = 1;    // similarity operand from the float64 front end (k_frames64); 0 = from k_stft's fp32 magnitudes
+    int topk_force_exact = 0;  // test knob: every column of REPET-SIM goes through the exact float64 fallback
 };
 extern repet_tuning g_repet_tuning;
 
@@ -159,8 +160,12 @@ void launch_frames64(cudaStream_t st, const float* audio, const double* audio64,
 // tcgen05 / TMEM / TMA self-similarity GEMM (repet_simgemm.cu); returns 0 on success
 int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_items, int T, float* S, int sm_count);
 void launch_selfsim_simt(cudaStream_t st, const float* An32, int n_items, int T, float* S);
+// overflow: [4] ints zeroed by the caller ([0] = columns handed to the exact fallback, [1..3] statistics);
+// ovf_cols: [n_items * T] ints; scratch: topk_exact_scratch_bytes(T, sm_count) bytes
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
-                int number, int* idx_out, int* cnt_out, int* overflow);
+                int number, int* idx_out, int* cnt_out, int* overflow, int* ovf_cols, unsigned char* scratch,
+                int sm_count);
+size_t topk_exact_scratch_bytes(int T, int sm_count);
 // returns 0, or nonzero when the device refuses the shared memory / scratch the ring needs
 int launch_online_select(cudaStream_t st, const double* An64, int n_items, int T, int B, int frame_base, double thr,
                          int d, int number, int* idx_out, int* cnt_out);

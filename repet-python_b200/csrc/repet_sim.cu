@@ -325,7 +325,8 @@ __device__ __forceinline__ int topk_bin(float v) {
 
 __global__ void __launch_bounds__(TOPK_THREADS)
 k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, float tau, double thr, int d, int number,
-       int nb, int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ overflow) {
+       int nb, int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ overflow,
+       int* __restrict__ ovf_cols, int force_exact) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* s_col = reinterpret_cast<double*>(smem);           // [APITCH64]   column c, float64
     double* s_exact = s_col + APITCH64;                        // [TOPK_CAP]   exact similarity of candidates
@@ -340,6 +341,10 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const float* __restrict__ row = S + ((size_t)item * T + c) * (size_t)T;
     const double* __restrict__ A = An64 + (size_t)item * T * APITCH64;
+    if (force_exact) {  // test knob: every column goes through k_topk_exact
+        if (t == 0) ovf_cols[atomicAdd(overflow, 1)] = item * T + c;
+        return;
+    }
     if (t == 0) {
         s_count = 0;
         s_kept = 0;
@@ -414,8 +419,11 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     __syncthreads();
     int count = s_count;
     if (count > TOPK_CAP) {
-        if (t == 0) atomicExch(overflow, 1);
-        count = TOPK_CAP;
+        // more near-tied candidates than the certification budget holds (a stationary or exactly looped stretch:
+        // thousands of similarities within 2 tau of each other): the column is handed to k_topk_exact, which
+        // applies the reference's rule to an exact float64 row
+        if (t == 0) ovf_cols[atomicAdd(overflow, 1)] = item * T + c;
+        return;
     }
     if (t == 0) atomicAdd(overflow + 1, count);  // statistics: candidates proposed
     // ---- prune: only the `number` best survive the ranking ---------------------------------------
@@ -554,8 +562,73 @@ k_topk(const float* __restrict__ S, const double* __restrict__ An64, int T, floa
     if (t == 0) cnt_out[(size_t)item * T + c] = min(s_kept, number);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_topk_exact  --  _localmaxima on an exact float64 similarity row           repet.py:1294-1345
+// The columns k_topk could not settle within its candidate budget.  A persistent CTA walks the list: the whole
+// row <A[c], A[u]>, u < T, as exact float64 dots (global scratch), then the reference's rule verbatim -- v >= thr,
+// strictly above every neighbour within +-d (windows clipped, NaN never wins), survivors ranked by value
+// descending (ties: descending index) -- with no tolerance anywhere.
+// ------------------------------------------------------------------------------------------
+constexpr int TOPK_EXACT_CTAS_PER_SM = 2;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+k_topk_exact(const double* __restrict__ An64, int T, double thr, int d, int number, const int* __restrict__ overflow,
+             const int* __restrict__ ovf_cols, unsigned char* __restrict__ scratch, size_t per_cta,
+             int* __restrict__ idx_out, int* __restrict__ cnt_out) {
+    __shared__ double s_col[APITCH64];
+    __shared__ int s_kept;
+    const int n_cols = overflow[0];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
+    double* __restrict__ row = reinterpret_cast<double*>(scratch + (size_t)blockIdx.x * per_cta);  // [T]
+    int* __restrict__ kept = reinterpret_cast<int*>(row + T);                                     // [T]
+    for (int e = blockIdx.x; e < n_cols; e += gridDim.x) {
+        const int col = ovf_cols[e];
+        const int item = col / T, c = col - item * T;
+        const double* __restrict__ A = An64 + (size_t)item * T * APITCH64;
+        __syncthreads();  // the previous column's ranking has finished with row / kept / s_col
+        if (t == 0) s_kept = 0;
+        for (int k = t; k < APITCH64; k += blockDim.x) s_col[k] = A[(size_t)c * APITCH64 + k];
+        __syncthreads();
+        for (int u = warp; u < T; u += nwarp) {
+            const double v = warp_dot64(s_col, A + (size_t)u * APITCH64, lane);
+            if (lane == 0) row[u] = v;
+        }
+        __syncthreads();
+        for (int i = t; i < T; i += blockDim.x) {
+            const double v = row[i];
+            bool keep = v >= thr;
+            const int lo = max(i - d, 0), hi = min(i + d, T - 1);
+            for (int u = lo; u <= hi && keep; ++u)
+                if (u != i && !(v > row[u])) keep = false;
+            if (keep) kept[atomicAdd(&s_kept, 1)] = i;
+        }
+        __syncthreads();
+        const int K = s_kept;
+        for (int q = t; q < K; q += blockDim.x) {
+            const int i = kept[q];
+            const double v = row[i];
+            int rank = 0;
+            for (int r = 0; r < K; ++r) {
+                const int io = kept[r];
+                const double vo = row[io];
+                rank += (vo > v) || (vo == v && io > i);
+            }
+            if (rank < number) idx_out[((size_t)item * T + c) * (size_t)number + rank] = i;
+        }
+        if (t == 0) cnt_out[(size_t)item * T + c] = min(K, number);
+    }
+}
+
+size_t topk_exact_scratch_bytes(int T, int sm_count) {
+    const size_t per_cta = ((size_t)T * 12 + 255) / 256 * 256;
+    return per_cta * (size_t)(sm_count * TOPK_EXACT_CTAS_PER_SM);
+}
+
+// ovf_cols: [n_items * T] ints; scratch: topk_exact_scratch_bytes(T, sm_count) bytes; overflow[0] counts the
+// columns handed to the exact kernel (zeroed by the caller)
 int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items, int T, float tau, double thr, int d,
-                int number, int* idx_out, int* cnt_out, int* overflow) {
+                int number, int* idx_out, int* cnt_out, int* overflow, int* ovf_cols, unsigned char* scratch,
+                int sm_count) {
     // blocks of d elements per chunk: as many as fit, at least halo + one payload block
     int nb = 3;
     if (d > 0) {
@@ -566,7 +639,11 @@ int launch_topk(cudaStream_t st, const float* S, const double* An64, int n_items
     static SmemOptIn opt_in;
     smem_opt_in(k_topk, smem, opt_in);
     dim3 grid(T, n_items);
-    k_topk<<<grid, TOPK_THREADS, smem, st>>>(S, An64, T, tau, thr, d, number, nb, idx_out, cnt_out, overflow);
+    k_topk<<<grid, TOPK_THREADS, smem, st>>>(S, An64, T, tau, thr, d, number, nb, idx_out, cnt_out, overflow, ovf_cols,
+                                             g_tuning.topk_force_exact);
+    const size_t per_cta = ((size_t)T * 12 + 255) / 256 * 256;
+    k_topk_exact<<<sm_count * TOPK_EXACT_CTAS_PER_SM, TOPK_THREADS, 0, st>>>(An64, T, thr, d, number, overflow, ovf_cols,
+                                                                            scratch, per_cta, idx_out, cnt_out);
     return 0;
 }
 

@@ -279,6 +279,9 @@ def _stft(audio_signal, window_function, step_length):
         audio_stft: audio STFT (window_length, number_times), full mirrored spectrum
     """
     audio_signal = np.asarray(audio_signal)
+    if not _host.fast_stft_applies(len(window_function), step_length):
+        # any window length and step (repet.py:1018-1058 puts no constraint on them): float64 general path
+        return _host.stft_general(audio_signal, window_function, step_length)
     half = _host.stft_half(audio_signal[np.newaxis, :], window_function, step_length)[0]  # (T, F)
     window_length = len(window_function)
     audio_stft = np.empty((window_length, half.shape[0]), dtype=complex)
@@ -301,6 +304,8 @@ def _istft(audio_stft, window_function, step_length):
     """
     audio_stft = np.asarray(audio_stft, dtype=complex)
     window_length = audio_stft.shape[0]
+    if not _host.fast_stft_applies(window_length, step_length) or len(window_function) != window_length:
+        return _host.istft_general(audio_stft, window_function, step_length)
     half = window_length // 2
     # real(ifft(Y)) only sees the Hermitian part of Y: Yh[k] = (Y[k] + conj(Y[N-k]))/2
     mirror = np.conj(audio_stft[(-np.arange(window_length)) % window_length, :])

@@ -112,6 +112,11 @@ SIGNATURES = {
     "repet_spectrogram_frames": (_c_int, [_pp, _c_i64]),
     "repet_spectrogram_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp]),
     "repet_foreground_dev": (_c_int, [_vp, _vp, _vp, _c_i64, _vp]),
+    "repet_stft_frames": (_c_int, [_c_i64, _c_int, _c_int]),
+    "repet_stft_f64": (_c_int, [_vp, _vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp]),
+    "repet_istft_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _c_int, _vp, ctypes.POINTER(_c_i64)]),
+    "repet_acorr_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
+    "repet_beatspectrum_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
     "repet_stft": (_c_int, [_vp, _vp, _c_int, _c_i64, _vp, _vp, _vp]),
     "repet_istft": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_double, _vp]),
     "repet_beatspectrum": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
@@ -435,9 +440,76 @@ def istft_half(spectrum, window_function, step_length, handle=None):
     return signal
 
 
-def beatspectrum(audio_spectrogram, handle=None):
-    """_beatspectrum (repet.py:1142-1158): (F, T) magnitudes -> float64 (T,)."""
+FAST_WINDOWS = (512, 1024, 2048)  # window lengths of the register-blocked fp32 frame transforms
+
+
+def fast_stft_applies(window_length, step_length):
+    return window_length in FAST_WINDOWS and 2 * step_length == window_length
+
+
+def stft_general(audio_signal, window_function, step_length, handle=None):
+    """_stft (repet.py:1001-1060) for ANY window length and step, float64 on the device: (S,) -> complex128
+    (window_length, number_times), every bin, the reference's own layout."""
     handle = handle or get_handle()
+    signal = np.ascontiguousarray(audio_signal, dtype=np.float64)
+    window = np.ascontiguousarray(window_function, dtype=np.float64)
+    if signal.ndim != 1 or window.ndim != 1:
+        raise ValueError("audio_signal and window_function must be one-dimensional")
+    window_length, step_length = len(window), int(step_length)
+    number_times = handle.lib.repet_stft_frames(len(signal), window_length, step_length)
+    audio_stft = np.empty((window_length, max(number_times, 0)), dtype=np.complex128)
+    frames = ctypes.c_int32(0)
+    handle.check(handle.lib.repet_stft_f64(handle.h, _ptr(signal), len(signal), _ptr(window), window_length, step_length,
+                                           _ptr(audio_stft), ctypes.byref(frames)))
+    assert frames.value == number_times
+    return audio_stft
+
+
+def istft_general(audio_stft, window_function, step_length, handle=None):
+    """_istft (repet.py:1063-1105) for ANY window length and step, float64 on the device: complex (window_length,
+    number_times) -> float64 (number_times * step - (window_length - step),)."""
+    handle = handle or get_handle()
+    spectrum = np.ascontiguousarray(audio_stft, dtype=np.complex128)
+    window = np.ascontiguousarray(window_function, dtype=np.float64)
+    window_length, number_times = spectrum.shape
+    if len(window) != window_length:
+        raise ValueError("operands could not be broadcast together (window length differs from the STFT's)")
+    step_length = int(step_length)
+    number_samples = max(0, number_times * step_length - (window_length - step_length))
+    signal = np.empty(number_samples, dtype=np.float64)
+    produced = _c_i64(0)
+    handle.check(handle.lib.repet_istft_f64(handle.h, _ptr(spectrum), window_length, number_times, _ptr(window), step_length,
+                                            _ptr(signal), ctypes.byref(produced)))
+    assert produced.value == number_samples
+    return signal
+
+
+def acorr_general(data_matrix, handle=None):
+    """_acorr (repet.py:1108-1139) for any number of rows, float64 on the device."""
+    handle = handle or get_handle()
+    data = np.ascontiguousarray(data_matrix, dtype=np.float64)
+    rows, columns = data.shape
+    out = np.empty((rows, columns), dtype=np.float64)
+    handle.check(handle.lib.repet_acorr_f64(handle.h, _ptr(data), rows, columns, _ptr(out)))
+    return out
+
+
+def beatspectrum_general(audio_spectrogram, handle=None):
+    """_beatspectrum (repet.py:1142-1158) for any size, float64 on the device: (F, T) -> (T,)."""
+    handle = handle or get_handle()
+    spectrogram = np.ascontiguousarray(audio_spectrogram, dtype=np.float64)
+    number_frequencies, number_times = spectrogram.shape
+    beat = np.empty(number_times, dtype=np.float64)
+    handle.check(handle.lib.repet_beatspectrum_f64(handle.h, _ptr(spectrogram), number_frequencies, number_times, _ptr(beat)))
+    return beat
+
+
+def beatspectrum(audio_spectrogram, handle=None):
+    """_beatspectrum (repet.py:1142-1158): (F, T) magnitudes -> float64 (T,).  Spectrograms that fit the drivers'
+    fp32 beat kernel (T <= 1024 frames, F <= 1025) go through it; anything larger takes the float64 general path."""
+    handle = handle or get_handle()
+    if np.shape(audio_spectrogram)[1] > 1024 or np.shape(audio_spectrogram)[0] > 1025:
+        return beatspectrum_general(audio_spectrogram, handle=handle)
     spectrogram = np.ascontiguousarray(np.asarray(audio_spectrogram).T, dtype=np.float32)  # time major
     number_times, number_rows = spectrogram.shape
     beat = np.empty(number_times, dtype=np.float64)
@@ -932,6 +1004,8 @@ def simmask(audio_spectrogram, similarity_indices, handle=None):
 def acorr(data_matrix, handle=None):
     """_acorr (repet.py:1108-1139): unbiased autocorrelation of every column, (rows, cols) -> float64."""
     handle = handle or get_handle()
+    if 2 * np.shape(data_matrix)[0] - 1 > 2048:
+        return acorr_general(data_matrix, handle=handle)  # more rows than the drivers' 2048-point transform holds
     data = np.ascontiguousarray(data_matrix, dtype=np.float32)
     rows, columns = data.shape
     out = np.empty((rows, columns), dtype=np.float64)

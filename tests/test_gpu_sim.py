@@ -192,3 +192,39 @@ def test_c_stream_matches_the_host_side_stream_bit_for_bit(repet):
     short.process(np.full((3 * FS, 2), 0.01))
     with pytest.raises(ValueError):
         short.flush()
+
+
+def test_exact_fallback_gives_the_reference_lists(repet):
+    """a column with more near-tied candidates than the certification budget used to raise
+    NotImplementedError; it now goes through k_topk_exact (exact float64 row + the reference's rule).  Forced for every
+    column of the 2-minute golden track: all 5169 lists (set and order) must still equal the reference's."""
+    import os
+
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_long.npz"))
+    spec = make_golden.SIM_LONG
+    x = make_golden.sim_long_input()
+    repet._host.set_tuning(topk_force_exact=1)
+    try:
+        y, lists = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    finally:
+        repet._host.set_tuning(topk_force_exact=0)
+    assert np.array_equal(np.array([len(v) for v in lists]), golden["counts"].astype(np.int64))
+    assert np.array_equal(make_golden.list_digests(lists, spec["block"]), golden["digests"])
+    assert np.all(np.isfinite(y))
+
+
+def test_stationary_track_overflows_the_candidate_budget_and_still_matches(repet):
+    """A steady chord with a little noise: every frame resembles every other to within 2 tau, so each column of the
+    similarity matrix proposes T > 2048 candidates -- the data-dependent case that used to be refused.  Lists must
+    equal the oracle's (the exact similarities differ by ~1e-9, far above float64 rounding)."""
+    seconds = 56  # T = 2413 frames > the 2048-candidate budget
+    n = seconds * FS
+    time = np.arange(n) / FS
+    rng = np.random.default_rng(77)
+    tone = sum(a * np.sin(2 * np.pi * f * time + p) for a, f, p in ((0.3, 220.0, 0.1), (0.2, 440.0, 1.0), (0.1, 1320.0, 2.0)))
+    x = np.stack([tone, 0.8 * tone], axis=1) + 1e-4 * rng.standard_normal((n, 2))
+    y, lists = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    y_ref, det = oracle.sim(x, FS, return_details=True)
+    bad = [i for i, (a, b) in enumerate(zip(lists, det["indices"])) if not np.array_equal(a, b)]
+    assert not bad, "lists differ at frames %s" % bad[:8]
+    _assert_signal(y, y_ref, "stationary track")
