@@ -212,6 +212,7 @@ int repet_set_tuning(const char* name, int value) {
     else if (key == "copy_chunk_mb") g_repet_tuning.copy_chunk_mb = value;
     else if (key == "cert_rel_ppm") g_repet_tuning.cert_rel_ppm = value;
     else if (key == "topk_force_exact") g_repet_tuning.topk_force_exact = value;
+    else if (key == "simgemm_bn") g_repet_tuning.simgemm_bn = value;
     else return REPET_E_INVALID_ARG;
     return REPET_OK;
 }

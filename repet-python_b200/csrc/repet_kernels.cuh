@@ -24,6 +24,7 @@ struct repet_tuning {
     int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
     int copy_chunk_mb = 128; // host-buffer entry points: megabytes per copy slot (pipeline granularity)
     int sim_frames64 = 1;    // similarity operand from the float64 front end (k_frames64); 0 = from k_stft's fp32 magnitudes
+    int simgemm_bn = 256;    // tile width of the split similarity GEMM: 256 (128 x 256 tiles) or 128 (square tiles)
     int topk_force_exact = 0;  // test knob: every column of REPET-SIM goes through the exact float64 fallback
 };
 extern repet_tuning g_repet_tuning;

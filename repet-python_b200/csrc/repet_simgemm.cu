@@ -12,8 +12,8 @@
 //   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (TMEM -> registers), transpose through a padded
 //               smem tile so that global stores are 128-byte coalesced rows, predicated on the
 //               ragged edges; overlaps the next tile's MMAs through the second accumulator
-// With square tiles (split configuration) only the upper triangle of tiles is computed; the epilogue writes
-// every off-diagonal tile and its mirror image.
+// In the split configuration only the tiles that reach the diagonal or lie above it are computed; the epilogue
+// writes every element above the diagonal and its mirror image.
 // The result only PROPOSES similar-frame candidates: k_topk certifies every decision with exact
 // float64 dot products, with tau covering the TF32 rounding (|S~ - S| <= 2 * 2^-11 + accumulation).
 #include "repet_kernels.cuh"
@@ -41,7 +41,7 @@ constexpr int GEMM_THREADS = 192;
 //                fp32-class accuracy for 3x the MMAs)
 template <int BN, bool SPLIT3>
 struct GemmCfg {
-    static constexpr int STAGES = SPLIT3 ? 3 : 4;
+    static constexpr int STAGES = SPLIT3 ? (BN == 256 ? 2 : 3) : 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (A_BYTES + B_BYTES);
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
@@ -120,9 +120,43 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // Tile schedule.  S = A A^T is symmetric: with square tiles (the split configuration) only the tiles on and
 // above the diagonal are computed and the epilogue writes each off-diagonal tile twice (once mirrored), which
-// halves the MMAs.  Upper-triangle tiles are numbered row by row: row mi starts at mi*nt - mi*(mi-1)/2.
-template <bool TRI>
-__device__ __forceinline__ void decode_tile(int tile, int mt, int nt, int& item, int& mi, int& ni) {
+// halves the MMAs.
+// L2-aware raster: the operands of a 10-minute track (2 x 109 MB of hi / lo rows) do not fit the 126 MB L2, and a
+// row-by-row walk of the triangle re-read every B block once per tile row (ncu, profiles/r2a_sim: 13.2 GB of DRAM
+// reads for 218 MB of operands, L2 hit rate 61 %).  The triangle is cut into BANDS of RASTER_G tile rows; inside a
+// band the tile COLUMN is the slow index and the row the fast one, so the 148 tiles in flight share the band's
+// RASTER_G A blocks and ~10 B blocks (~28 MB) and every operand block comes from DRAM once per band.
+constexpr int RASTER_G = 16;
+
+// Triangle of tiles BM rows x BN columns, Q = BN / BM (1 or 2): tile (mi, nj) is computed iff it holds an element
+// on or above the diagonal, i.e. nj >= mi / Q.  Band b holds tile rows [G b, G b + rb) and tile columns from
+// c0 = (G / Q) b; its column c0 + c crosses rows r <= Q c + Q - 1, i.e. min(rb, Q (c + 1)) tiles.
+template <int Q>
+__host__ __device__ inline int band_tiles(int mt, int nt, int band, int* rb_out) {
+    const int rb = min(RASTER_G, mt - RASTER_G * band);
+    if (rb_out) *rb_out = rb;
+    if (rb <= 0) return 0;
+    const int nb = nt - (RASTER_G / Q) * band;
+    int count = 0;
+    for (int c = 0; c < nb; ++c) {
+        const int h = min(rb, Q * (c + 1));
+        if (h == rb) {
+            count += (nb - c) * rb;
+            break;
+        }
+        count += h;
+    }
+    return count;
+}
+template <int Q>
+__host__ __device__ inline int triangle_tiles(int mt, int nt) {
+    int total = 0;
+    for (int band = 0; RASTER_G * band < mt; ++band) total += band_tiles<Q>(mt, nt, band, nullptr);
+    return total;
+}
+
+template <bool TRI, int Q>
+__device__ __forceinline__ void decode_tile(int tile, int per_item, int mt, int nt, int& item, int& mi, int& ni) {
     if (!TRI) {
         item = tile / (mt * nt);
         const int rem = tile - item * (mt * nt);
@@ -130,23 +164,34 @@ __device__ __forceinline__ void decode_tile(int tile, int mt, int nt, int& item,
         ni = rem - mi * nt;
         return;
     }
-    const int per_item = nt * (nt + 1) / 2;
     item = tile / per_item;
-    const int u = tile - item * per_item;
-    const float b = (float)(2 * nt + 1);
-    int r = (int)((b - sqrtf(fmaxf(b * b - 8.f * (float)u, 0.f))) * 0.5f);
-    r = max(0, min(nt - 1, r));
-    while (r > 0 && r * nt - r * (r - 1) / 2 > u) --r;
-    while (r + 1 < nt && (r + 1) * nt - (r + 1) * r / 2 <= u) ++r;
-    mi = r;
-    ni = r + (u - (r * nt - r * (r - 1) / 2));
+    int u = tile - item * per_item;
+    int band = 0, rb = 0;
+    for (;; ++band) {
+        const int count = band_tiles<Q>(mt, nt, band, &rb);
+        if (u < count || rb <= 0) break;
+        u -= count;
+    }
+    int c = 0;
+    for (;; ++c) {  // the columns that cross the diagonal (at most RASTER_G / Q of them), then full columns
+        const int h = min(rb, Q * (c + 1));
+        if (h == rb) {
+            c += u / rb;
+            u -= (u / rb) * rb;
+            break;
+        }
+        if (u < h) break;
+        u -= h;
+    }
+    mi = RASTER_G * band + u;
+    ni = (RASTER_G / Q) * band + c;
 }
 
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, int T, int n_items,
-          float* __restrict__ S) {
+          int per_item, float* __restrict__ S) {
     using Cfg = GemmCfg<BN, SPLIT3>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int B_BYTES = Cfg::B_BYTES;
@@ -164,9 +209,10 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr bool TRI = BM == BN;
+    constexpr bool TRI = SPLIT3;  // the split configuration forms the triangle only
+    constexpr int Q = BN / BM;
     const int mt = (T + BM - 1) / BM, nt = (T + BN - 1) / BN;
-    const int tiles_total = n_items * (TRI ? nt * (nt + 1) / 2 : mt * nt);
+    const int tiles_total = n_items * per_item;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -196,7 +242,7 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
                 int item, mi, ni;
-                decode_tile<TRI>(tile, mt, nt, item, mi, ni);
+                decode_tile<TRI, Q>(tile, per_item, mt, nt, item, mi, ni);
                 const int m0 = mi * BM, n0 = ni * BN;
                 for (int kb = 0; kb < KBLOCKS; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -251,9 +297,12 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++tile_iter) {
             int item, mi, ni;
-            decode_tile<TRI>(tile, mt, nt, item, mi, ni);
+            decode_tile<TRI, Q>(tile, per_item, mt, nt, item, mi, ni);
             const int m0 = mi * BM, n0 = ni * BN;
-            const bool mirror = TRI && ni != mi;
+            // every element of S is written exactly once: (row, col) with col >= row directly, its mirror image
+            // from the same registers; the part of a diagonal-crossing tile below the diagonal is dropped
+            const bool crosses = TRI && n0 < m0 + BM;  // the tile holds elements on or below the diagonal
+            const bool mirror = TRI && n0 + BN > m0 + 1;
             const uint32_t acc = tile_iter & 1;
             mbar_wait(&acc_full[acc], (tile_iter >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -270,9 +319,10 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     // S[col][row] = S[row][col]: for a fixed column the 32 lanes hold 32 consecutive rows, so the
                     // mirrored tile goes out as 128-byte rows straight from the registers
                     float* __restrict__ dst = Sitem + (size_t)(n0 + chunk * 32) * T + row_base + lane;
+                    const int above = row_base + lane - (n0 + chunk * 32);  // column offsets > above lie above the diagonal
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
-                        if (n0 + chunk * 32 + c < T) dst[(size_t)c * T] = __uint_as_float(v[c]);
+                        if (n0 + chunk * 32 + c < T && (!crosses || c > above)) dst[(size_t)c * T] = __uint_as_float(v[c]);
                 }
                 __syncwarp();
                 const int col = n0 + chunk * 32 + lane;
@@ -280,7 +330,7 @@ k_simgemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll 4
                     for (int r = 0; r < 32; ++r) {
                         const int row = row_base + r;
-                        if (row < T) Sitem[(size_t)row * T + col] = stage[r * EPI_PITCH + lane];
+                        if (row < T && (!crosses || col >= row)) Sitem[(size_t)row * T + col] = stage[r * EPI_PITCH + lane];
                     }
                 }
                 __syncwarp();
@@ -336,9 +386,10 @@ int launch_gemm(cudaStream_t st, const float* hi, const float* lo, int n_items, 
         if (!smem_opt_in(k_simgemm<BN, SPLIT3>, (size_t)Cfg::SMEM, opt_in)) return -2;
     }
     const int mt = (T + BM - 1) / BM, nt = (T + BN - 1) / BN;
-    const int tiles_total = n_items * (BM == BN ? nt * (nt + 1) / 2 : mt * nt);
+    const int per_item = SPLIT3 ? triangle_tiles<BN / BM>(mt, nt) : mt * nt;
+    const int tiles_total = n_items * per_item;
     const int grid = std::max(1, std::min(tiles_total, sm_count));
-    k_simgemm<BN, SPLIT3><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(map_a, map_b, map_a_lo, map_b_lo, T, n_items, S);
+    k_simgemm<BN, SPLIT3><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(map_a, map_b, map_a_lo, map_b_lo, T, n_items, per_item, S);
     return 0;
 }
 
@@ -347,7 +398,12 @@ int launch_gemm(cudaStream_t st, const float* hi, const float* lo, int n_items, 
 // S[item] = A[item] A[item]^T for n_items stacked [T][KPAD] operands.  `lo` = nullptr: single TF32 pass
 // on `hi`; otherwise the 3xTF32 split product of hi + lo.  Returns 0 on success.
 int launch_selfsim_tc(cudaStream_t st, const float* hi, const float* lo, int n_items, int T, float* S, int sm_count) {
-    if (lo) return launch_gemm<128, true>(st, hi, lo, n_items, T, S, sm_count);
+    // split product: 128 x 256 tiles (65 flop per operand byte from L2 instead of 49: the kernel runs at the L2
+    // throughput cap, ncu profiles/r2a_sim); "simgemm_bn" = 128 selects the round-1 square tiles
+    if (lo) {
+        if (g_tuning.simgemm_bn == 128) return launch_gemm<128, true>(st, hi, lo, n_items, T, S, sm_count);
+        return launch_gemm<256, true>(st, hi, lo, n_items, T, S, sm_count);
+    }
     return launch_gemm<256, false>(st, hi, nullptr, n_items, T, S, sm_count);
 }
 
