@@ -296,6 +296,17 @@ int repet_acorr_f64(repet_handle* h, const double* data, int n_rows, int n_colum
 /* _beatspectrum (repet.py:1142-1158), any size: spectrogram[n_frequencies][n_times] float64 -> beat[n_times]. */
 int repet_beatspectrum_f64(repet_handle* h, const double* spectrogram, int n_frequencies, int n_times, double* beat);
 
+/* ---- general float64 drivers ---------------------------------------------------------------
+ * repet.original / extended / adaptive / sim / simonline (repet.py:67-911; method 0..4) for the inputs the fast fp32
+ * kernels are not compiled for: window lengths other than 512 / 1024 / 2048 (sampling rates above 51.2 kHz: 4096
+ * points at 96 kHz, 8192 at 192 kHz, repet.py:130), any number of channels (repet.py:152-155), period ranges above
+ * 1024 frames, segments longer than one beat transform.  float64 end to end on the device (integer decisions need no
+ * certification), built for generality, not speed.  audio / background: (n_samples, n_channels) float64, HOST;
+ * window: the analysis window (window_length doubles, HOST); ints_host as repet_ints_per_clip(method, p, n_samples). */
+int repet_general_f64(repet_handle* h, int method, const double* audio, int64_t n_samples, int n_channels,
+                      const repet_params* p, const double* window, double* background, int32_t* ints_host,
+                      int64_t ints_capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,23 @@ RATE_CASES = {
 }
 
 
+# inputs outside the fast kernels' shapes, served by the general float64 path (repet_general.cu): window lengths 4096
+# and 8192 (96 / 192 kHz, repet.py:130), more than two channels (repet.py:152-155 loops over any number), and a period
+# range beyond 1024 frames.  Written to drivers_general.npz.
+GENERAL_CASES = {
+    "synth96k_13s": dict(kind="synth", fs=96000, index=41, samples=13 * 96000 + 11, channels=2,
+                         functions=["original", "adaptive", "sim", "simonline"]),
+    "synth96k_17s": dict(kind="synth", fs=96000, index=42, samples=17 * 96000, channels=2, functions=["extended"]),
+    "synth192k_5s": dict(kind="synth", fs=192000, index=43, samples=5 * 192000 + 3, channels=1, functions=["original", "sim"]),
+    "synth44k_3ch_12s": dict(kind="synth", index=45, samples=12 * FS + 100, channels=3,
+                             functions=["original", "extended", "adaptive", "sim", "simonline"]),
+    "synth44k_5ch_8s": dict(kind="synth", index=47, samples=8 * FS + 9, channels=5, functions=["original", "adaptive", "sim"]),
+    "synth16k_4ch_13s": dict(kind="synth", fs=16000, index=49, samples=13 * 16000, channels=4, functions=["original", "simonline"]),
+}
+# period range above 1024 frames (period_range[1] = 30 s -> 1292 frames at 44.1 kHz) on a 100 s clip
+LONG_PERIOD = dict(index=51, samples=100 * FS, channels=2, period_range=[1, 30])
+
+
 # a 2-minute track for REPET-SIM (T = 5169 frames, ~394k list entries): long enough that some pairs of
 # similarities are tied to ~1e-8 -- an fp32 analysis front end flips list 3619 -- and the float64 input is
 # deliberately NOT representable in fp32 (1e-9 dither), as a user's array would be.  Stored as per-list
@@ -190,6 +207,29 @@ def pin_drivers(ref, cases, wav=None):
     return drivers
 
 
+def pin_general(ref, provenance):
+    general = pin_drivers(ref, GENERAL_CASES)
+    # the long period range: a module tunable of the reference, restored afterwards
+    spec = LONG_PERIOD
+    x = repet_synth.make_clip(spec["index"], spec["samples"], spec["channels"]).T.astype(np.float64)
+    saved = ref.period_range
+    ref.period_range = list(spec["period_range"])
+    try:
+        y_ref = ref.original(x, FS)
+    finally:
+        ref.period_range = saved
+    y_orc, det = oracle.original(x, FS, return_details=True, period_range=tuple(spec["period_range"]))
+    _close(y_ref, y_orc, "long_period/original")
+    general["long_period/original/rms"] = np.sqrt(np.mean(np.square(y_ref)))
+    general["long_period/original/max"] = np.max(np.abs(y_ref))
+    general["long_period/original/dec"] = y_ref[::DECIMATE].copy()
+    general["long_period/original/period"] = np.int64(det["period"])
+    print("long_period/original period %d pinned" % det["period"])
+    for k, v in provenance.items():
+        general["provenance/" + k] = np.array(v)
+    np.savez_compressed(os.path.join(GOLDEN, "drivers_general.npz"), **general)
+
+
 def main():
     warnings.simplefilter("ignore")
     ref = reference_shim.load()
@@ -210,6 +250,9 @@ def main():
 
     if "--sim-long-only" in sys.argv:
         pin_sim_long(ref)
+        return
+    if "--general-only" in sys.argv:
+        pin_general(ref, provenance)
         return
     # ---- helper-level cases -----------------------------------------------------------
     h = helper_inputs()
@@ -261,6 +304,7 @@ def main():
         rates["provenance/" + k] = np.array(v)
     np.savez_compressed(os.path.join(GOLDEN, "drivers_rates.npz"), **rates)
     pin_sim_long(ref)
+    pin_general(ref, provenance)
     sizes = {f: os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN)}
     print("written:", sizes)
 

@@ -420,3 +420,577 @@ int repet_beatspectrum_f64(repet_handle* h, const double* spectrogram, int n_fre
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// General float64 DRIVERS: repet.original / extended / adaptive / sim / simonline (repet.py:67-911) for the inputs the
+// register-blocked fp32 kernels are not compiled for -- window lengths other than 512 / 1024 / 2048 (sampling rates
+// above 51.2 kHz: 4096 points at 96 kHz, 8192 at 192 kHz, repet.py:130), more than two channels (the reference
+// loops over any number, repet.py:152-155), period ranges above 1024 frames, segments longer than one beat transform,
+// very long similar-frame lists.  Same pipeline, written for generality instead of speed: float64 end to end (so the
+// integer decisions need no certification), simple kernels, transforms by the Stockham passes above.
+// =====================================================================================================================
+namespace {
+
+enum { GEN_ORIGINAL = 0, GEN_EXTENDED = 1, GEN_ADAPTIVE = 2, GEN_SIM = 3, GEN_SIMONLINE = 4 };
+
+struct Pool {  // device allocations of one call, released together
+    std::vector<void*> ptrs;
+    bool ok = true;
+    template <typename T>
+    T* get(size_t n) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ok = false;
+            return nullptr;
+        }
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    void release(void* p) {
+        for (size_t i = 0; i < ptrs.size(); ++i)
+            if (ptrs[i] == p) {
+                cudaFree(p);
+                ptrs.erase(ptrs.begin() + i);
+                return;
+            }
+    }
+    ~Pool() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+
+// frames[c][j][n] = w[n] * x[j*H + n - pad][c]  (zero outside the signal); audio (S, C) interleaved, row pitch `ld`
+__global__ void k_gen_frames(const double* __restrict__ audio, long long S, int C, int ld, const double* __restrict__ window,
+                             int N, int H, int pad, long long T, double2* __restrict__ frames) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)C * T * N) return;
+    const int n = (int)(gid % N);
+    const long long j = (gid / N) % T;
+    const int c = (int)(gid / ((long long)N * T));
+    const long long m = j * H + n - pad;
+    frames[gid] = make_double2((m >= 0 && m < S) ? window[n] * audio[m * ld + c] : 0.0, 0.0);
+}
+// V[c][t][f] = |X[c][t][f]|, f <= N/2 (repet.py:158); Vm[t][f] = mean over channels (repet.py:162, 667)
+__global__ void k_gen_magnitude(const double2* __restrict__ X, int C, long long T, int N, int F, double* __restrict__ V,
+                                double* __restrict__ Vm) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= T * F) return;
+    const long long t = gid / F;
+    const int f = (int)(gid - t * F);
+    double sum = 0.0;
+    for (int c = 0; c < C; ++c) {
+        const double2 x = X[((long long)c * T + t) * N + f];
+        const double v = hypot(x.x, x.y);
+        V[((long long)c * T + t) * F + f] = v;
+        sum += v;
+    }
+    Vm[gid] = sum / (double)C;
+}
+// time sequences of the squared channel-mean magnitudes, one per (segment, frequency): z[(s*F + f)][l] =
+// Vm[ts_s + l][f]^2 for l < len and 0 <= ts_s + l < T, else 0          (repet.py:162, 1123, 1177-1198)
+__global__ void k_gen_load_seq(const double* __restrict__ Vm, long long T, int F, int f0, int nf, long long ts0, int seg_step,
+                               int n_seg, int len, int L, double2* __restrict__ z) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_seg * nf * L) return;
+    const int l = (int)(gid % L);
+    const int f = (int)((gid / L) % nf);
+    const int s = (int)(gid / ((long long)L * nf));
+    const long long t = ts0 + (long long)s * seg_step + l;
+    double v = 0.0;
+    if (l < len && t >= 0 && t < T) {
+        v = Vm[t * F + f0 + f];
+        v *= v;
+    }
+    z[gid] = make_double2(v, 0.0);
+}
+// beat[s][l] += sum over this chunk's frequency rows of acorr / (len - l)     (repet.py:1135-1137)
+__global__ void k_gen_accumulate_beat(const double2* __restrict__ z, int nf, int n_seg, int len, int L, int n_lags,
+                                      double* __restrict__ beat) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_seg * n_lags) return;
+    const int s = gid / n_lags, l = gid - s * n_lags;
+    double acc = beat[gid];
+    const double scale = 1.0 / (double)L / (double)(len - l);
+    for (int f = 0; f < nf; ++f) acc += z[((long long)s * nf + f) * L + l].x * scale;
+    beat[gid] = acc;
+}
+// period = first argmax over lags [lo, hi) + 1 (repet.py:1262-1289, quirks Q1, Q2); the common 1/F factor is omitted
+__global__ void k_gen_argmax(const double* __restrict__ beat, int n_seg, int n_lags, int lo, int hi, int* __restrict__ period) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const double* __restrict__ b = beat + (long long)s * n_lags;
+    int arg = lo;
+    double best = b[lo];
+    for (int l = lo + 1; l < hi; ++l)
+        if (b[l] > best) {
+            best = b[l];
+            arg = l;
+        }
+    period[s] = arg + 1;
+}
+// per-frame periods of the adaptive REPET with the all-zero column of quirk Q3 (repet.py:1194-1204)
+__global__ void k_gen_expand(const int* __restrict__ seg_period, long long T, int step, int lo, int* __restrict__ frame_period) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= T) return;
+    const long long s = j / step;
+    const bool zero_column = step > 1 && (j - s * step) == step - 1;
+    frame_period[j] = zero_column ? lo + 1 : seg_period[s];
+}
+// An[t][f] = Vm[t][f] / ||Vm[t]||  (repet.py:1220, 1240); an all-zero frame gives 0/0 = NaN as in the reference (Q18)
+__global__ void k_gen_normalize(const double* __restrict__ Vm, long long T, int F, double* __restrict__ An) {
+    const long long t = blockIdx.x;
+    __shared__ double s_red[256];
+    double acc = 0.0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const double v = Vm[t * F + f];
+        acc += v * v;
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double norm = sqrt(s_red[0]);
+    for (int f = threadIdx.x; f < F; f += blockDim.x) An[t * F + f] = Vm[t * F + f] / norm;
+}
+// S = An An^T, float64, 64 x 64 tiles; the k order is the same for (i, j) and (j, i): S is bitwise symmetric
+__global__ void __launch_bounds__(256)
+k_gen_gram(const double* __restrict__ An, long long T, int F, double* __restrict__ S) {
+    __shared__ double sa[16][65];
+    __shared__ double sb[16][65];
+    const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+    const long long i0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < F; k0 += 16) {
+        for (int e = 0; e < 4; ++e) {
+            const int idx = threadIdx.x + 256 * e;
+            const int row = idx >> 4, kk = idx & 15;
+            const long long ri = i0 + row, rj = j0 + row;
+            sa[kk][row] = (ri < T && k0 + kk < F) ? An[ri * F + k0 + kk] : 0.0;
+            sb[kk][row] = (rj < T && k0 + kk < F) ? An[rj * F + k0 + kk] : 0.0;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < 16; ++kk) {
+            double av[4], bv[4];
+            for (int a = 0; a < 4; ++a) av[a] = sa[kk][ti + 16 * a];
+            for (int b = 0; b < 4; ++b) bv[b] = sb[kk][tj + 16 * b];
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            const long long i = i0 + ti + 16 * a, j = j0 + tj + 16 * b;
+            if (i < T && j < T) S[j * T + i] = acc[a][b];
+        }
+}
+// _localmaxima of one vector held in shared memory (repet.py:1309-1343): v >= thr and strictly above every neighbour
+// within +-d (windows clipped, NaN never wins), ranked by value descending (ties: descending index), first `number`.
+// `kept` is scratch for n ints.  slot_frame (optional) maps a position to the frame index written out (simonline).
+__device__ void gen_localmaxima(const double* __restrict__ v, int n, double thr, int d, int number, int* __restrict__ kept,
+                                int* __restrict__ s_count, int* __restrict__ idx_out, int* __restrict__ cnt_out, int j_online,
+                                int B_online) {
+    if (threadIdx.x == 0) *s_count = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = v[i];
+        bool keep = x >= thr;
+        const int lo = max(i - d, 0), hi = min(i + d, n - 1);
+        for (int u = lo; u <= hi && keep; ++u)
+            if (u != i && !(x > v[u])) keep = false;
+        if (keep) kept[atomicAdd(s_count, 1)] = i;
+    }
+    __syncthreads();
+    const int K = *s_count;
+    for (int q = threadIdx.x; q < K; q += blockDim.x) {
+        const int i = kept[q];
+        const double x = v[i];
+        int rank = 0;
+        for (int r = 0; r < K; ++r) {
+            const int io = kept[r];
+            rank += (v[io] > x) || (v[io] == x && io > i);
+        }
+        if (rank < number) {
+            int out = i;
+            if (B_online > 0) {  // ring slot -> frame index (repet.py:837, 852; quirk Q6)
+                const int j0 = j_online % B_online;
+                out = i <= j0 ? j_online - (j0 - i) : j_online - (j0 - i) - B_online;
+            }
+            idx_out[rank] = out;
+        }
+    }
+    if (threadIdx.x == 0) *cnt_out = min(K, number);
+    __syncthreads();
+}
+// REPET-SIM: the similar-frame list of every column of S (repet.py:1370-1381); one CTA per column, row in smem
+__global__ void __launch_bounds__(512)
+k_gen_indices(const double* __restrict__ S, int T, double thr, int d, int number, int* __restrict__ idx, int* __restrict__ cnt) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    double* v = reinterpret_cast<double*>(gsm);
+    int* kept = reinterpret_cast<int*>(v + T);
+    __shared__ int s_count;
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) v[i] = S[(long long)c * T + i];
+    __syncthreads();
+    gen_localmaxima(v, T, thr, d, number, kept, &s_count, idx + (long long)c * number, cnt + c, 0, 0);
+}
+// online REPET-SIM: frame j >= B-1 against the B frames of its ring buffer in SLOT order (repet.py:834-866, quirk Q6)
+__global__ void __launch_bounds__(256)
+k_gen_online(const double* __restrict__ An, int T, int F, int B, double thr, int d, int number, int* __restrict__ idx,
+             int* __restrict__ cnt) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    double* v = reinterpret_cast<double*>(gsm);       // [B] similarity by slot
+    int* kept = reinterpret_cast<int*>(v + B);        // [B]
+    __shared__ int s_count;
+    const int j = blockIdx.x + (B - 1);
+    if (j >= T) return;
+    const int j0 = j % B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double* __restrict__ a = An + (long long)j * F;
+    for (int b = warp; b < B; b += nwarp) {
+        const int u = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
+        const double* __restrict__ x = An + (long long)u * F;
+        double acc = 0.0;
+        for (int f = lane; f < F; f += 32) acc = fma(a[f], x[f], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) v[b] = acc;
+    }
+    __syncthreads();
+    gen_localmaxima(v, B, thr, d, number, kept, &s_count, idx + (long long)j * number, cnt + j, j, B);
+}
+
+// median of n values fetched by `fetch(s)`: insertion sort in local memory up to GEN_SORT_MAX, exact rank selection
+// beyond; np.median's even-count rule (mean of the two middle values); n = 0 gives NaN (np.median of an empty slice)
+constexpr int GEN_SORT_MAX = 128;
+template <typename Fetch>
+__device__ double gen_median(int n, Fetch fetch) {
+    if (n <= 0) return nan("");
+    if (n <= GEN_SORT_MAX) {
+        double v[GEN_SORT_MAX];
+        for (int s = 0; s < n; ++s) {
+            const double x = fetch(s);
+            int q = s;
+            while (q > 0 && v[q - 1] > x) {
+                v[q] = v[q - 1];
+                --q;
+            }
+            v[q] = x;
+        }
+        return (n & 1) ? v[n >> 1] : 0.5 * (v[(n >> 1) - 1] + v[n >> 1]);
+    }
+    const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
+    double v_lo = 0.0, v_hi = 0.0;
+    bool got_lo = false, got_hi = false;
+    for (int i = 0; i < n && !(got_lo && got_hi); ++i) {
+        const double vi = fetch(i);
+        int less = 0, equal = 0;
+        for (int s = 0; s < n; ++s) {
+            const double vs = fetch(s);
+            less += vs < vi;
+            equal += vs == vi;
+        }
+        if (!got_lo && less <= k_lo && k_lo < less + equal) {
+            v_lo = vi;
+            got_lo = true;
+        }
+        if (!got_hi && less <= k_hi && k_hi < less + equal) {
+            v_hi = vi;
+            got_hi = true;
+        }
+    }
+    return 0.5 * (v_lo + v_hi);
+}
+
+// repeating model + soft mask + high-pass + mirror + apply, in place on X (repet.py:1398-1456, 1474-1506, 1529-1543,
+// 185-197).  mode 0: period-strided frames of a phase (quirk Q9); 1: the in-range frames t + c p_t; 2: listed frames.
+__global__ void k_gen_mask_apply(double2* __restrict__ X, const double* __restrict__ V, int C, long long T, int N, int F,
+                                 int mode, int period, const int* __restrict__ frame_period, int order,
+                                 const int* __restrict__ idx, const int* __restrict__ cnt, int number, int first_frame,
+                                 int cutoff) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)C * T * F) return;
+    const int f = (int)(gid % F);
+    const long long t = (gid / F) % T;
+    const int c = (int)(gid / ((long long)F * T));
+    if (t < first_frame) return;  // online frames before the buffer is full are never synthesised (quirk Q5)
+    const double* __restrict__ Vc = V + (long long)c * T * F;
+    double model;
+    if (mode == 0) {
+        const int p = period;
+        const long long r = (T + p - 1) / p;
+        const long long q = t % p;
+        const int n = (int)(q < T - (r - 1) * p ? r : r - 1);
+        model = gen_median(n, [&](int s) { return Vc[(q + (long long)s * p) * F + f]; });
+    } else if (mode == 1) {
+        const int p = frame_period[t];
+        const int half = (order + 1) / 2;
+        long long c_lo = 1 - half, c_hi = order - half;
+        if (p > 0) {
+            c_lo = max(c_lo, -(t / p));
+            c_hi = min(c_hi, (T - 1 - t) / p);
+        } else {
+            c_lo = c_hi = 0;
+        }
+        const int n = (int)(c_hi - c_lo + 1);
+        model = gen_median(n, [&](int s) { return Vc[(t + (c_lo + s) * p) * F + f]; });
+    } else {
+        const int n = cnt[t];
+        const int* __restrict__ list = idx + t * number;
+        model = gen_median(n, [&](int s) { return Vc[(long long)list[s] * F + f]; });
+    }
+    const double v = Vc[t * F + f];
+    const double eps = 2.220446049250313e-16;
+    double rep = (model != model) ? model : fmin(v, model);  // np.minimum keeps NaN
+    double m = (rep + eps) / (v + eps);
+    if (f >= 1 && f <= cutoff) m = 1.0;  // high-pass rows 1..cutoff, DC kept (quirk Q11)
+    double2* __restrict__ row = X + ((long long)c * T + t) * N;
+    double2 x = row[f];
+    row[f] = make_double2(m * x.x, m * x.y);
+    if (f >= 1 && f < N - f) {  // mirrored bin N - f (repet.py:188-190); f = N/2 is its own mirror
+        x = row[N - f];
+        row[N - f] = make_double2(m * x.x, m * x.y);
+    }
+}
+// overlap-add of real(ifft) frames of every channel, interleaved output (repet.py:1089-1103, 898-909).
+// trim = samples dropped at the start (N - H for centred frames, 0 online); frames below first_frame are skipped.
+__global__ void k_gen_overlap_add(const double2* __restrict__ frames, int C, long long T, int N, int H, long long trim,
+                                  int first_frame, long long S, double inv_norm, double* __restrict__ out, int ld) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= S * C) return;
+    const long long m = gid / C;
+    const int c = (int)(gid - m * C);
+    const long long pos = m + trim;
+    long long j_hi = pos / H;
+    if (j_hi > T - 1) j_hi = T - 1;
+    long long j_lo = pos - N + 1 <= 0 ? 0 : (pos - N + H) / H;
+    if (j_lo < first_frame) j_lo = first_frame;
+    double acc = 0.0;
+    for (long long j = j_lo; j <= j_hi; ++j) acc += frames[((long long)c * T + j) * N + (pos - j * H)].x;
+    out[m * ld + c] = acc * inv_norm;
+}
+// one step of the reference's in-place cross-fade (repet.py:388-414)
+__global__ void k_gen_xfade(double* __restrict__ bg, const double* __restrict__ seg, long long k, long long len, long long ov,
+                            int C, int first) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= len * C) return;
+    const long long i = gid / C;
+    double* __restrict__ dst = bg + k * C + gid;
+    if (!first && i < ov) {
+        const double up = (double)(2 * i + 1) / (double)(2 * ov);                 // triang(2 ov)[i]
+        const double down = (double)(2 * (ov - 1 - i) + 1) / (double)(2 * ov);    // triang(2 ov)[ov + i]
+        *dst = *dst * down + seg[gid] * up;
+    } else {
+        *dst += seg[gid];
+    }
+}
+
+struct GenShape {
+    int N, H, F, C;
+    const double* d_window;
+    double gain;
+};
+
+// the beat spectra of n_seg segments (rows [ts0 + s*seg_step, ... + len) of Vm^2, zero outside the clip), lags < n_lags
+int gen_beat(repet_handle* h, Pool& pool, const GenShape& g, const double* Vm, long long T, long long ts0, int seg_step,
+             int n_seg, int len, int n_lags, double* beat) {
+    cudaStream_t st = h->stream;
+    const int L = next_pow2((long long)len + n_lags);
+    CU(cudaMemsetAsync(beat, 0, (size_t)n_seg * n_lags * sizeof(double), st));
+    // (segments x frequency rows) in chunks of at most ~1 GB per transform buffer
+    const size_t row_bytes = (size_t)L * sizeof(double2);
+    const int seg_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_seg, ((size_t)1 << 30) / (row_bytes * g.F)));
+    const int f_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)g.F, ((size_t)1 << 30) / (row_bytes * seg_chunk)));
+    double2* z = pool.get<double2>((size_t)seg_chunk * f_chunk * L);
+    double2* tmp = pool.get<double2>((size_t)seg_chunk * f_chunk * L);
+    if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general beat spectrum");
+    for (int s0 = 0; s0 < n_seg; s0 += seg_chunk) {
+        const int ns = std::min(seg_chunk, n_seg - s0);
+        for (int f0 = 0; f0 < g.F; f0 += f_chunk) {
+            const int nf = std::min(f_chunk, g.F - f0);
+            const long long total = (long long)ns * nf * L;
+            k_gen_load_seq<<<blocks_for(total), 256, 0, st>>>(Vm, T, g.F, f0, nf, ts0 + (long long)s0 * seg_step, seg_step, ns,
+                                                              len, L, z);
+            fft_pow2(st, z, tmp, L, (long long)ns * nf, false);
+            k_power<<<blocks_for(total), 256, 0, st>>>(z, total);
+            fft_pow2(st, z, tmp, L, (long long)ns * nf, true);
+            k_gen_accumulate_beat<<<blocks_for((long long)ns * n_lags, 128), 128, 0, st>>>(z, nf, ns, len, L, n_lags,
+                                                                                          beat + (size_t)s0 * n_lags);
+            h->launches += 3 + 2 * 16;
+        }
+    }
+    pool.release(z);
+    pool.release(tmp);
+    return REPET_OK;
+}
+
+// One clip (or one segment of `extended`) through the pipeline.  d_audio: (S, C) float64 with row pitch ld on the
+// device; d_out: same layout; d_ints: integer outputs of `method` on the device.
+int gen_run(repet_handle* h, int method, const double* d_audio, long long S, int ld, const GenShape& g,
+            const repet_params* p, double* d_out, int* d_ints) {
+    cudaStream_t st = h->stream;
+    Pool pool;
+    const int N = g.N, H = g.H, F = g.F, C = g.C;
+    const bool online = method == GEN_SIMONLINE;
+    long long T;
+    int pad, first_frame = 0;
+    if (online) {
+        const int B = p->buffer_frames;
+        if (B < 1) return fail(h, REPET_E_INVALID_ARG, "buffer_length must cover at least one frame");
+        if (S < N || (long long)(B - 2) * H + N > S)  // the reference's warm-up loop fails to broadcast (repet.py:801-804)
+            return fail(h, REPET_E_INVALID_ARG, "operands could not be broadcast together (signal shorter than the buffer)");
+        T = (S - N + H - 1) / H + 1;  // repet.py:781
+        pad = 0;
+        first_frame = B - 1;
+    } else {
+        T = (S + H - 1) / H + 1;  // repet.py:1018-1028 with N = 2H
+        pad = N / 2;
+    }
+    if (T > 2000000000LL / std::max(N, 1)) return fail(h, REPET_E_UNSUPPORTED, "clip too long for the general path");
+    double2* X = pool.get<double2>((size_t)C * T * N);
+    double2* tmp = pool.get<double2>((size_t)C * T * N);
+    double* V = pool.get<double>((size_t)C * T * F);
+    double* Vm = pool.get<double>((size_t)T * F);
+    if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+    k_gen_frames<<<blocks_for((long long)C * T * N), 256, 0, st>>>(d_audio, S, C, ld, g.d_window, N, H, pad, T, X);
+    fft_pow2(st, X, tmp, N, (long long)C * T, false);
+    k_gen_magnitude<<<blocks_for(T * F), 256, 0, st>>>(X, C, T, N, F, V, Vm);
+    h->launches += 2 + 13;
+
+    int mode = 0, period_host = 0, *frame_period = nullptr, *idx = nullptr, *cnt = nullptr;
+    if (method == GEN_ORIGINAL) {
+        const int lag_hi = (int)std::min<long long>(p->period_hi, T / 3);  // quirk Q2
+        if (p->period_lo < 0 || lag_hi <= p->period_lo)
+            return fail(h, REPET_E_TOO_SHORT, "attempt to get argmax of an empty sequence (signal too short for the period range)");
+        double* beat = pool.get<double>(lag_hi);
+        if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+        int rc = gen_beat(h, pool, g, Vm, T, 0, 0, 1, (int)T, lag_hi, beat);
+        if (rc) return rc;
+        k_gen_argmax<<<1, 32, 0, st>>>(beat, 1, lag_hi, p->period_lo, lag_hi, d_ints);
+        CU(cudaMemcpyAsync(&period_host, d_ints, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        mode = 0;
+    } else if (method == GEN_ADAPTIVE) {
+        const int L = p->segment_length, step = p->segment_step;
+        if (L <= 0 || step <= 0) return fail(h, REPET_E_INVALID_ARG, "segment length and step must be positive");
+        if (p->filter_order < 1) return fail(h, REPET_E_INVALID_ARG, "filter_order must be at least 1");
+        const int lag_hi = std::min(p->period_hi, L / 3);
+        if (p->period_lo < 0 || lag_hi <= p->period_lo)
+            return fail(h, REPET_E_TOO_SHORT, "attempt to get argmax of an empty sequence (segment too short for the period range)");
+        const int n_seg = (int)((T + step - 1) / step);
+        const int left = L / 2;  // ceil((L - 1) / 2), repet.py:1182
+        double* beat = pool.get<double>((size_t)n_seg * lag_hi);
+        int* seg_period = pool.get<int>(n_seg);
+        if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+        int rc = gen_beat(h, pool, g, Vm, T, -left, step, n_seg, L, lag_hi, beat);
+        if (rc) return rc;
+        k_gen_argmax<<<blocks_for(n_seg, 128), 128, 0, st>>>(beat, n_seg, lag_hi, p->period_lo, lag_hi, seg_period);
+        k_gen_expand<<<blocks_for(T), 256, 0, st>>>(seg_period, T, step, p->period_lo, d_ints);
+        frame_period = d_ints;
+        mode = 1;
+    } else if (method == GEN_SIM || online) {
+        if (p->similarity_number < 1) return fail(h, REPET_E_INVALID_ARG, "similarity_number must be at least 1");
+        if (p->similarity_distance < 0) return fail(h, REPET_E_INVALID_ARG, "similarity_distance must not be negative");
+        const int number = p->similarity_number;
+        double* An = pool.get<double>((size_t)T * F);
+        if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+        k_gen_normalize<<<(unsigned)T, 256, 0, st>>>(Vm, T, F, An);
+        cnt = d_ints;
+        idx = d_ints + T;
+        CU(cudaMemsetAsync(cnt, 0, (size_t)T * sizeof(int), st));
+        if (online) {
+            const int B = p->buffer_frames;
+            const size_t smem = (size_t)B * 12 + 16;
+            if (smem > 200 * 1024) return fail(h, REPET_E_UNSUPPORTED, "buffer_length too long for the general online selection");
+            if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gen_online, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (T > B - 1)
+                k_gen_online<<<(unsigned)(T - (B - 1)), 256, smem, st>>>(An, (int)T, F, B, p->similarity_threshold,
+                                                                        p->similarity_distance, number, idx, cnt);
+        } else {
+            double* Sm = pool.get<double>((size_t)T * T);
+            if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory for the similarity matrix");
+            dim3 grid((unsigned)((T + 63) / 64), (unsigned)((T + 63) / 64));
+            k_gen_gram<<<grid, 256, 0, st>>>(An, T, F, Sm);
+            const size_t smem = (size_t)T * 12 + 16;
+            if (smem > 220 * 1024) return fail(h, REPET_E_UNSUPPORTED, "track too long for the general similar-frame selection");
+            if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gen_indices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_gen_indices<<<(unsigned)T, 512, smem, st>>>(Sm, (int)T, p->similarity_threshold, p->similarity_distance, number, idx, cnt);
+            pool.release(Sm);
+        }
+        mode = 2;
+    } else {
+        return fail(h, REPET_E_INVALID_ARG, "unknown method");
+    }
+    k_gen_mask_apply<<<blocks_for((long long)C * T * F), 256, 0, st>>>(X, V, C, T, N, F, mode, period_host, frame_period,
+                                                                      p->filter_order, idx, cnt, p->similarity_number,
+                                                                      first_frame, p->cutoff_bins);
+    fft_pow2(st, X, tmp, N, (long long)C * T, true);
+    k_gen_overlap_add<<<blocks_for(S * C), 256, 0, st>>>(X, C, T, N, H, online ? 0 : N - H, first_frame, S,
+                                                        1.0 / ((double)N * g.gain), d_out, ld);
+    h->launches += 4 + 13;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int repet_general_f64(repet_handle* h, int method, const double* audio, int64_t n_samples, int n_channels,
+                      const repet_params* p, const double* window, double* background, int32_t* ints_host,
+                      int64_t ints_capacity) {
+    if (!h) return REPET_E_INVALID_ARG;
+    if (!audio || !p || !window || !background || n_samples < 1 || n_channels < 1)
+        return fail(h, REPET_E_INVALID_ARG, "bad buffer or size");
+    const int N = p->window_length, H = p->step_length;
+    if (N < 4 || (N & (N - 1)) || 2 * H != N)
+        return fail(h, REPET_E_INVALID_ARG, "window_length must be a power of two and step_length half of it (repet.py:130-132)");
+    if (method < GEN_ORIGINAL || method > GEN_SIMONLINE) return fail(h, REPET_E_INVALID_ARG, "unknown method");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Pool pool;
+    const long long S = n_samples;
+    const int C = n_channels;
+    const long long need = repet_ints_per_clip(method, p, n_samples);
+    if (ints_host && ints_capacity < need) return fail(h, REPET_E_INVALID_ARG, "integer output buffer too small");
+    double* d_audio = pool.get<double>((size_t)S * C);
+    double* d_out = pool.get<double>((size_t)S * C);
+    double* d_window = pool.get<double>(N);
+    int* d_ints = pool.get<int>((size_t)std::max<long long>(need, 1));
+    if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+    CU(cudaMemcpyAsync(d_audio, audio, (size_t)S * C * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_window, window, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+    GenShape g{N, H, N / 2 + 1, C, d_window, p->cola_gain};
+    int rc = REPET_OK;
+    if (method == GEN_EXTENDED && S >= (long long)p->segment_length + p->segment_step) {
+        // repet.py:263-419: `original` per segment, the last one takes the remainder, cross-faded in order
+        const long long seg_len = p->segment_length, step = p->segment_step, ov = seg_len - step;
+        if (seg_len <= 0 || step <= 0 || ov <= 0) return fail(h, REPET_E_INVALID_ARG, "segment_length must exceed segment_step (both positive)");
+        const int n_seg = 1 + (int)((S - seg_len) / step);
+        const long long last_len = S - (long long)(n_seg - 1) * step;
+        double* d_seg = pool.get<double>((size_t)std::max(seg_len, last_len) * C);
+        if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+        CU(cudaMemsetAsync(d_out, 0, (size_t)S * C * sizeof(double), st));
+        long long k = 0;
+        for (int j = 0; j < n_seg && !rc; ++j, k += step) {
+            const long long len = j < n_seg - 1 ? seg_len : last_len;
+            rc = gen_run(h, GEN_ORIGINAL, d_audio + k * C, len, C, g, p, d_seg, d_ints + j);
+            if (!rc) k_gen_xfade<<<blocks_for(len * C), 256, 0, st>>>(d_out, d_seg, k, len, ov, C, j == 0 ? 1 : 0);
+        }
+    } else {
+        rc = gen_run(h, method == GEN_EXTENDED ? GEN_ORIGINAL : method, d_audio, S, C, g, p, d_out, d_ints);
+    }
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(background, d_out, (size_t)S * C * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ints_host && need > 0) CU(cudaMemcpyAsync(ints_host, d_ints, (size_t)need * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return REPET_OK;
+}
+
+}  // extern "C"

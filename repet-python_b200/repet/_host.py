@@ -112,6 +112,7 @@ SIGNATURES = {
     "repet_spectrogram_frames": (_c_int, [_pp, _c_i64]),
     "repet_spectrogram_batch_dev": (_c_int, [_vp, _vp, _c_int, _c_int, _c_i64, _pp, _vp]),
     "repet_foreground_dev": (_c_int, [_vp, _vp, _vp, _c_i64, _vp]),
+    "repet_general_f64": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _pp, _vp, _vp, _vp, _c_i64]),
     "repet_stft_frames": (_c_int, [_c_i64, _c_int, _c_int]),
     "repet_stft_f64": (_c_int, [_vp, _vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp]),
     "repet_istft_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _c_int, _vp, ctypes.POINTER(_c_i64)]),
@@ -328,10 +329,53 @@ def number_of_frames(number_samples, window_length, step_length):
 # ------------------------------------------------------------------------------------------
 # drivers
 # ------------------------------------------------------------------------------------------
+FAST_WINDOWS = (512, 1024, 2048)  # window lengths of the register-blocked fp32 frame transforms
+
+
+def needs_general_path(params, number_channels):
+    """Inputs the fast fp32 kernels are not compiled for: sampling rates above 51.2 kHz (window 4096 at 96 kHz, 8192
+    at 192 kHz, repet.py:130) and more than two channels.  They run on the general float64 device path
+    (repet_general_f64); so does anything else the fast path answers with REPET_E_UNSUPPORTED (period ranges above
+    1024 frames, ...)."""
+    return params.window_length not in FAST_WINDOWS or number_channels > 2
+
+
+def general_f64(method, audio_signal, sampling_frequency, tunables, handle=None):
+    """Any of the five drivers on the general float64 device path.  Returns (background float64 (S, C), ints int32)."""
+    number_samples, number_channels = np.shape(audio_signal)
+    handle = handle or get_handle()
+    params, window_function = derive_params(sampling_frequency, tunables, method)
+    audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
+    window = np.ascontiguousarray(window_function, dtype=np.float64)
+    background = np.empty((number_samples, number_channels), dtype=np.float64)
+    capacity = int(handle.lib.repet_ints_per_clip(METHODS[method], ctypes.byref(params), number_samples))
+    ints = np.zeros(max(1, capacity), dtype=np.int32)
+    handle.check(
+        handle.lib.repet_general_f64(
+            handle.h, METHODS[method], _ptr(audio), number_samples, number_channels, ctypes.byref(params), _ptr(window),
+            _ptr(background), _ptr(ints), len(ints),
+        )
+    )
+    return background, ints[:capacity]
+
+
 def original_f64(audio_signal, sampling_frequency, tunables, handle=None, return_period=False):
     """repet.original with the reference's calling convention (repet.py:67-202)."""
     number_samples, number_channels = np.shape(audio_signal)  # repet.py:125 (ValueError if not 2-D)
     handle = handle or get_handle()
+    params, window_function = derive_params(sampling_frequency, tunables)
+    if needs_general_path(params, number_channels):
+        background, ints = general_f64("original", audio_signal, sampling_frequency, tunables, handle=handle)
+        return (background, int(ints[0])) if return_period else background
+    try:
+        return _original_f64_fast(audio_signal, sampling_frequency, tunables, handle, return_period)
+    except NotImplementedError:  # e.g. a period range above 1024 frames: the general path has no such limit
+        background, ints = general_f64("original", audio_signal, sampling_frequency, tunables, handle=handle)
+        return (background, int(ints[0])) if return_period else background
+
+
+def _original_f64_fast(audio_signal, sampling_frequency, tunables, handle, return_period):
+    number_samples, number_channels = np.shape(audio_signal)
     params, window_function = derive_params(sampling_frequency, tunables)
     handle.ensure_window(params.window_length)
     audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
@@ -356,6 +400,9 @@ def original_batch(audio, sampling_frequency, tunables, handle=None, out=None):
         raise ValueError("audio must have shape (clips, channels, samples)")
     number_clips, number_channels, number_samples = audio.shape
     params, _ = derive_params(sampling_frequency, tunables)
+    if needs_general_path(params, number_channels):
+        background, ints = _separate_batch_general("original", audio, 0, 0, sampling_frequency, tunables, handle, out)
+        return background, ints[:, 0]
     handle.ensure_window(params.window_length)
     background = out if out is not None else np.empty_like(audio)
     periods = np.zeros(number_clips, dtype=np.int32)
@@ -438,9 +485,6 @@ def istft_half(spectrum, window_function, step_length, handle=None):
     gain = float(sum(window_function[0:window_length:step_length]))
     handle.check(handle.lib.repet_istft(handle.h, _ptr(packed), number_channels, number_times, gain, _ptr(signal)))
     return signal
-
-
-FAST_WINDOWS = (512, 1024, 2048)  # window lengths of the register-blocked fp32 frame transforms
 
 
 def fast_stft_applies(window_length, step_length):
@@ -554,6 +598,18 @@ def _single_f64(entry, driver, audio_signal, sampling_frequency, tunables, handl
     number_samples, number_channels = np.shape(audio_signal)  # ValueError if not 2-D, as in the reference
     handle = handle or get_handle()
     params, _ = derive_params(sampling_frequency, tunables, driver)
+    if needs_general_path(params, number_channels):
+        ints_capacity(params, number_samples)  # (lets the caller record the frame count)
+        return general_f64(driver, audio_signal, sampling_frequency, tunables, handle=handle)
+    try:
+        return _single_f64_fast(entry, driver, audio_signal, sampling_frequency, tunables, handle, ints_capacity)
+    except NotImplementedError:
+        return general_f64(driver, audio_signal, sampling_frequency, tunables, handle=handle)
+
+
+def _single_f64_fast(entry, driver, audio_signal, sampling_frequency, tunables, handle, ints_capacity):
+    number_samples, number_channels = np.shape(audio_signal)
+    params, _ = derive_params(sampling_frequency, tunables, driver)
     handle.ensure_window(params.window_length)
     audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
     background = np.empty((number_samples, number_channels), dtype=np.float64)
@@ -583,7 +639,20 @@ def separate_f64(method, audio_signal, sampling_frequency, tunables, handle=None
     number_samples, number_channels = np.shape(audio_signal)
     handle = handle or get_handle()
     lib = handle.lib
-    params, _ = derive_params(sampling_frequency, tunables, method)
+    params, window_function = derive_params(sampling_frequency, tunables, method)
+    if needs_general_path(params, number_channels):
+        # general float64 path: the by-products are formed from its outputs (foreground = audio - background,
+        # README.md:68; spectrograms by the general _stft, README.md:79-81)
+        audio = np.asarray(audio_signal, dtype=np.float64)
+        background, ints = general_f64(method, audio, sampling_frequency, tunables, handle=handle)
+        result = {"background": background, "foreground": audio - background, "integers": ints}
+        if spectrograms:
+            half = params.window_length // 2 + 1
+            for name, signal in (("audio_spectrogram", audio), ("background_spectrogram", background),
+                                 ("foreground_spectrogram", result["foreground"])):
+                result[name] = np.abs(stft_general(np.mean(signal, axis=1), window_function, params.step_length,
+                                                   handle=handle)[0:half, :])
+        return result
     handle.ensure_window(params.window_length)
     audio = np.ascontiguousarray(audio_signal, dtype=np.float64)
     background = np.empty((number_samples, number_channels), dtype=np.float64)
@@ -669,6 +738,10 @@ def driver_batch(driver, audio, sampling_frequency, tunables, handle=None):
         raise ValueError("audio must have shape (clips, channels, samples)")
     number_clips, number_channels, number_samples = audio.shape
     params, _ = derive_params(sampling_frequency, tunables, driver)
+    if driver not in METHODS:
+        raise ValueError("unknown driver %r" % driver)
+    if needs_general_path(params, number_channels):
+        return _separate_batch_general(driver, audio, 0, 0, sampling_frequency, tunables, handle, None)
     handle.ensure_window(params.window_length)
     if driver == "original":
         per_clip = 1
@@ -767,6 +840,8 @@ def separate_batch(driver, audio, sampling_frequency, tunables, handle=None, in_
         number_clips, number_channels, number_samples = audio.shape
     params, _ = derive_params(sampling_frequency, tunables, driver)
     lib = load_library()
+    if needs_general_path(params, number_channels):
+        return _separate_batch_general(driver, audio, in_code, out_code, sampling_frequency, tunables, handle, out)
     per_clip = int(lib.repet_ints_per_clip(METHODS[driver], ctypes.byref(params), number_samples))
     out_shape = (number_clips, number_samples, number_channels) if out_code else (number_clips, number_channels, number_samples)
     out_dtype = np.int16 if out_code else np.float32
@@ -808,6 +883,24 @@ def separate_batch(driver, audio, sampling_frequency, tunables, handle=None, in_
     if errors:
         raise errors[0]
     return out, ints
+
+
+def _separate_batch_general(driver, audio, in_code, out_code, sampling_frequency, tunables, handle, out):
+    """separate_batch for inputs outside the fast kernels' shapes: clip by clip on the general float64 path."""
+    backgrounds, integers = [], []
+    for clip in audio:
+        x = clip.astype(np.float64) / 32768.0 if in_code else clip.T.astype(np.float64)  # repet.py:929
+        y, ints = general_f64(driver, x, sampling_frequency, tunables, handle=handle)
+        if out_code:
+            backgrounds.append(np.clip(np.rint(y.astype(np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16))
+        else:
+            backgrounds.append(np.ascontiguousarray(y.T.astype(np.float32)))
+        integers.append(ints)
+    result = np.stack(backgrounds) if backgrounds else np.zeros((0,) + audio.shape[1:], np.int16 if out_code else np.float32)
+    if out is not None:
+        out[...] = result
+        result = out
+    return result, np.stack(integers) if integers else np.zeros((0, 1), np.int32)
 
 
 def ragged_groups(shapes):

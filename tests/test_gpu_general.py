@@ -98,3 +98,103 @@ def test_beatspectrum_of_a_thirty_second_clip_gives_the_reference_period(repet):
     b = repet._beatspectrum(P)
     pr2 = oracle.period_range_frames([1, 10], FS, H)
     assert repet._periods(b, pr2) == oracle.periods(oracle.beatspectrum(P), pr2)
+
+
+# ---- general float64 DRIVERS (repet_general_f64) -----------------------------------------------------------------
+GENERAL_TOL = 1e-9  # float64 end to end: the only differences from the reference are summation orders
+
+
+@pytest.fixture(scope="module")
+def golden_general():
+    import os
+
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "drivers_general.npz")))
+
+
+def _signal_close(y, y_ref, what, tol=GENERAL_TOL):
+    assert y.shape == y_ref.shape, what
+    err = float(np.max(np.abs(y - y_ref))) / float(np.max(np.abs(y_ref)))
+    assert err <= tol, "%s: max-abs/peak %.3e" % (what, err)
+
+
+def _general_cases():
+    for case, spec in make_golden.GENERAL_CASES.items():
+        for fn in spec["functions"]:
+            yield case, fn
+
+
+@pytest.mark.parametrize("case,fn", list(_general_cases()))
+def test_general_drivers_match_the_reference(repet, golden_general, case, fn):
+    """96 kHz (4096-point window), 192 kHz (8192), 3 / 4 / 5 channels: the reference's outputs recorded by
+    oracle/make_golden.py (tests/golden/drivers_general.npz); integers bit-exact, signals to 1e-9 of the peak."""
+    import warnings
+
+    warnings.simplefilter("ignore")
+    spec = make_golden.GENERAL_CASES[case]
+    fs = make_golden.case_fs(spec)
+    x = make_golden.case_input(spec)
+    key = "%s/%s" % (case, fn)
+    tun = repet._tunables()
+    if fn == "original":
+        y, period = repet._host.original_f64(x, fs, tun, return_period=True)
+        assert period == int(golden_general[key + "/period"])
+    elif fn == "extended":
+        y, periods = repet._host.extended_f64(x, fs, tun, return_periods=True)
+        assert np.array_equal(periods, golden_general[key + "/periods"])
+    elif fn == "adaptive":
+        y, periods = repet._host.adaptive_f64(x, fs, tun, return_periods=True)
+        assert np.array_equal(periods, golden_general[key + "/periods"])
+    else:
+        f = repet._host.sim_f64 if fn == "sim" else repet._host.simonline_f64
+        y, lists = f(x, fs, tun, return_indices=True)
+        first = int(golden_general.get(key + "/first_frame", 0))
+        counts = np.array([len(v) for v in lists[first:]])
+        assert np.array_equal(counts, golden_general[key + "/index_counts"])
+        assert np.array_equal(np.concatenate(lists[first:]), golden_general[key + "/index_flat"])
+    _signal_close(y[:: make_golden.DECIMATE], golden_general[key + "/dec"], key + " (golden)")
+    # the drop-in names go the same way
+    assert np.array_equal(getattr(repet, fn)(x, fs), y, equal_nan=True)
+
+
+def test_general_path_agrees_with_the_fast_path_on_a_stereo_clip(repet):
+    """The two device implementations against each other where both apply (44.1 kHz stereo): same integers, signals
+    within the fast path's fp32 error."""
+    x = make_golden.case_input(make_golden.DRIVER_CASES["synth_12s"])
+    tun = repet._tunables()
+    for method in ("original", "extended", "adaptive", "sim", "simonline"):
+        y_general, ints_general = repet._host.general_f64(method, x, FS, tun)
+        y_ref = getattr(oracle, method)(x, FS)
+        _signal_close(y_general, y_ref, method + " general vs oracle")
+        y_fast = getattr(repet, method)(x, FS)
+        _signal_close(y_fast, y_general, method + " fast vs general", tol=1e-4)
+
+
+def test_period_range_above_1024_frames(repet, golden_general):
+    """period_range = [1, 30] s is 1292 frames at 44.1 kHz: beyond the fast beat transform, REPET_E_UNSUPPORTED inside,
+    the general path outside."""
+    spec = make_golden.LONG_PERIOD
+    x = repet_synth.make_clip(spec["index"], spec["samples"], spec["channels"]).T.astype(np.float64)
+    saved = repet.period_range
+    try:
+        repet.period_range = list(spec["period_range"])
+        y, period = repet._host.original_f64(x, FS, repet._tunables(), return_period=True)
+    finally:
+        repet.period_range = saved
+    assert period == int(golden_general["long_period/original/period"])
+    _signal_close(y[:: make_golden.DECIMATE], golden_general["long_period/original/dec"], "long period range")
+
+
+def test_general_batch_and_separate(repet):
+    """Batch and by-product entry points on three-channel clips."""
+    audio = repet_synth.make_batch(960, 2, 7 * FS, number_channels=3)
+    background, periods = repet.original_batch(audio, FS)
+    for i in range(2):
+        y_ref, det = oracle.original(audio[i].T.astype(np.float64), FS, return_details=True)
+        assert int(periods[i]) == det["period"]
+        _signal_close(background[i].T.astype(np.float64), y_ref, "3-channel batch clip %d" % i, tol=1e-6)
+    q, _ = repet.separate_batch(audio, FS, "original", out_format="pcm16")
+    assert q.shape == (2, 7 * FS, 3) and q.dtype == np.int16
+    parts = repet.separate(audio[0].T.astype(np.float64), FS, "adaptive")
+    y_ref = oracle.adaptive(audio[0].T.astype(np.float64), FS)
+    _signal_close(parts["background"], y_ref, "3-channel separate")
+    assert parts["background_spectrogram"].shape == (1025, parts["audio_spectrogram"].shape[1])

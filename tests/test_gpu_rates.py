@@ -135,8 +135,12 @@ def test_batch_other_sampling_rates(repet, fs):
     _assert_signal(repet.original(x, 44100), y_ref, "44.1 kHz after %d Hz" % fs)
 
 
-def test_unsupported_window_length_raises(repet):
-    with pytest.raises(NotImplementedError):
-        repet.original(np.zeros((4000, 1)) + 0.01, 4000)  # N = 256
-    with pytest.raises(NotImplementedError):
-        repet.original(np.zeros((200000, 1)) + 0.01, 96000)  # N = 4096
+def test_window_lengths_outside_the_fast_kernels_take_the_general_path(repet):
+    """Window lengths other than 512 / 1024 / 2048 used to raise NotImplementedError; they now run on the general
+    float64 device path (tests/test_gpu_general.py holds the golden cases at 96 and 192 kHz)."""
+    fs = 4000  # N = 256
+    x = repet_synth.make_clip(810, 9 * fs, 2, fs, 128).T.astype(np.float64)
+    y_ref, det = oracle.original(x, fs, return_details=True)
+    y, period = repet._host.original_f64(x, fs, repet._tunables(), return_period=True)
+    assert period == det["period"]
+    _assert_signal(y, y_ref, "4 kHz (256-point window)")
