@@ -42,7 +42,7 @@ def _stale():
 
 def _compile(job):
     src, win_n, obj, verbose = job
-    cmd = [NVCC] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd = [NVCC] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + os.environ.get("REPET_EXTRA_NVCC_FLAGS", "").split()
     if win_n:
         cmd += ["-DREPET_WIN_N=%d" % win_n]
     cmd += ["-c", os.path.join(CSRC, src), "-o", obj]

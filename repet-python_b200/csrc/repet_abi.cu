@@ -213,6 +213,7 @@ int repet_set_tuning(const char* name, int value) {
     else if (key == "cert_rel_ppm") g_repet_tuning.cert_rel_ppm = value;
     else if (key == "topk_force_exact") g_repet_tuning.topk_force_exact = value;
     else if (key == "simgemm_bn") g_repet_tuning.simgemm_bn = value;
+    else if (key == "adaptive_vsq") g_repet_tuning.adaptive_vsq = value;
     else return REPET_E_INVALID_ARG;
     return REPET_OK;
 }

@@ -235,6 +235,7 @@ int make_plan(repet_handle* h, int kind, const repet_params* p, int nch, int64_t
         b += align_up((size_t)plan->n_beat_seg * plan->beat_parts * BEAT_L * sizeof(float));
         b += align_up((size_t)plan->n_beat_seg * sizeof(int32_t));
         b += align_up((size_t)nch * plan->T * PPITCH * sizeof(float));
+        b += align_up((size_t)nch * plan->T * PPITCH * sizeof(float));               // squared magnitudes (adaptive_vsq)
         b += align_up((size_t)plan->n_beat_seg * (CERT_MAX + 1) * sizeof(int));       // period certification records
         b += align_up((size_t)plan->n_beat_seg * CERT_MAX * 16 * sizeof(double));
         b += 1024;
@@ -449,6 +450,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         float* psd = bump.take<float>((size_t)g * plan.n_beat_seg * plan.beat_parts * BEAT_L);
         int32_t* seg_period = bump.take<int32_t>((size_t)g * plan.n_beat_seg);
         float* model = bump.take<float>((size_t)g * nch * T * PPITCH);
+        float* Vsq = g_tuning.adaptive_vsq ? bump.take<float>((size_t)g * nch * T * PPITCH) : nullptr;
         int* cert = bump.take<int>((size_t)g * plan.n_beat_seg * (CERT_MAX + 1));
         double* cert_val = bump.take<double>((size_t)g * plan.n_beat_seg * CERT_MAX * 16);  // x CERT_TSPLIT partial sums
         int32_t* frame_period = ints + (size_t)clip0 * T;
@@ -458,7 +460,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         const int beat_L = beat_transform_length(plan.seg_frames, plan.lag_hi);
         {
             Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, P, P_POWER, K);
+            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, P, P_POWER, K, Vsq);
         }
         {
             // segment i spans frames [i - left_pad, i - left_pad + L) (zero outside), repet.py:1177-1198
@@ -476,7 +478,7 @@ int run_adaptive(repet_handle* h, const Plan& plan, const float* audio, int n_cl
         {
             Timed timed(h, REPET_K_MODEL, 2);
             launch_expand_periods(st, seg_period, g, plan.n_beat_seg, T, plan.step_frames, plan.p.period_lo, frame_period);
-            launch_adaptive_model(st, X, g, T, nch, frame_period, plan.p.filter_order, model);
+            launch_adaptive_model(st, X, g, T, nch, frame_period, plan.p.filter_order, model, Vsq);
         }
         {
             Timed timed(h, REPET_K_MASK_ISTFT);

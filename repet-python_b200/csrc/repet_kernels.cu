@@ -28,16 +28,22 @@ using TF = Fft<2048>;   // time-axis transforms of the beat spectrum
 // ------------------------------------------------------------------------------------------
 // one output bin of the Hermitian split: a = Z[k]/2, b = Z[2048-k]/2 (the window is pre-halved)
 //   XL[k] = a + conj(b)            XR[k] = -i (a - conj(b))
-template <int NCH>
+// VSQ: also write the squared magnitudes |X_c|^2 of every channel to vrow[c * PPITCH + k] (the adaptive median
+// gathers 5 rows per frame: 4-byte magnitudes halve its L2 traffic against the 8-byte spectra)
+template <int NCH, bool VSQ = false>
 __device__ __forceinline__ void stft_emit(float2 a, float2 b, int k, float2* __restrict__ xrow, float* __restrict__ prow,
-                                          int pmode) {
+                                          int pmode, float* __restrict__ vrow = nullptr) {
     const float2 xl = __ffma2_rn(b, make_float2(1.f, -1.f), a);
     xrow[k] = xl;
-    float mean = cmag(xl);
+    const float l2 = cmag2(xl);
+    float mean = fast_sqrt(l2);
+    if (VSQ) vrow[k] = l2;
     if (NCH == 2) {
         const float2 d = __ffma2_rn(b, make_float2(-1.f, 1.f), a);  // a - conj(b); XR = (d.y, -d.x)
         xrow[XPITCH + k] = make_float2(d.y, -d.x);
-        mean = 0.5f * (mean + cmag(d));
+        const float r2 = cmag2(d);
+        mean = 0.5f * (mean + fast_sqrt(r2));
+        if (VSQ) vrow[PPITCH + k] = r2;
     }
     if (prow) prow[k] = pmode == P_POWER ? mean * mean : mean;
 }
@@ -55,10 +61,10 @@ __device__ __forceinline__ void stft_emit_mixdown(float2 a, float2 b, int k, flo
     }
 }
 
-template <int NCH, int MINB, bool MIXDOWN = false>
+template <int NCH, int MINB, bool MIXDOWN = false, bool VSQ = false>
 __global__ void __launch_bounds__(FF::THREADS, MINB)
 k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window, FftTables tb,
-       float2* __restrict__ X, float* __restrict__ P, int pmode, int K) {
+       float2* __restrict__ X, float* __restrict__ P, int pmode, int K, float* __restrict__ Vsq = nullptr) {
     __shared__ float2 s_bufA[FF::BUF];
     __shared__ float2 s_bufB[FF::BUF];
     __shared__ float2 s_tw2[FF::TW2];
@@ -121,6 +127,7 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
         const size_t frame = (size_t)item * g.T + j;
         float2* __restrict__ xrow = X + frame * (size_t)(NCH * XPITCH);
         float* __restrict__ prow = P ? P + frame * (size_t)PPITCH : nullptr;
+        float* __restrict__ vrow = VSQ ? Vsq + frame * (size_t)(NCH * PPITCH) : nullptr;
         if (prow && t >= 1 && t < PPITCH - XPITCH) prow[XPITCH + t] = 0.f;  // rows 1025..1031: zero padding
         if (MIXDOWN) {
             if (t != 0) {
@@ -145,12 +152,20 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k3 = 0; k3 < 4; ++k3)
-                    stft_emit<NCH>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3], (h == 0 ? t : FF::CCOLS - t) + FF::CCOLS * k3, xrow, prow, pmode);
+                    stft_emit<NCH, VSQ>(r[h * 8 + k3], r[(1 - h) * 8 + 7 - k3], (h == 0 ? t : FF::CCOLS - t) + FF::CCOLS * k3, xrow, prow, pmode, vrow);
         } else {
             // thread 0 owns the self-mirrored columns 0 and 128; bin 0 packs (DC, Nyquist), both real
             const float2 dc = r[0], ny = r[4];
             xrow[0] = make_float2(2.f * dc.x, 2.f * ny.x);
             if (NCH == 2) xrow[XPITCH] = make_float2(2.f * dc.y, 2.f * ny.y);
+            if (VSQ) {
+                vrow[0] = __fmul_rn(2.f * dc.x, 2.f * dc.x);
+                vrow[XPITCH] = __fmul_rn(2.f * ny.x, 2.f * ny.x);
+                if (NCH == 2) {
+                    vrow[PPITCH] = __fmul_rn(2.f * dc.y, 2.f * dc.y);
+                    vrow[PPITCH + XPITCH] = __fmul_rn(2.f * ny.y, 2.f * ny.y);
+                }
+            }
             if (prow) {
                 const float m0 = NCH == 2 ? fabsf(dc.x) + fabsf(dc.y) : 2.f * fabsf(dc.x);
                 const float mn = NCH == 2 ? fabsf(ny.x) + fabsf(ny.y) : 2.f * fabsf(ny.x);
@@ -158,17 +173,22 @@ k_stft(const float* __restrict__ audio, Geom g, const float* __restrict__ window
                 prow[XPITCH] = pmode == P_POWER ? mn * mn : mn;
             }
 #pragma unroll
-            for (int k3 = 1; k3 < 4; ++k3) stft_emit<NCH>(r[k3], r[8 - k3], FF::CCOLS * k3, xrow, prow, pmode);
+            for (int k3 = 1; k3 < 4; ++k3) stft_emit<NCH, VSQ>(r[k3], r[8 - k3], FF::CCOLS * k3, xrow, prow, pmode, vrow);
 #pragma unroll
-            for (int k3 = 0; k3 < 4; ++k3) stft_emit<NCH>(r[8 + k3], r[8 + 7 - k3], FF::THREADS + FF::CCOLS * k3, xrow, prow, pmode);
+            for (int k3 = 0; k3 < 4; ++k3) stft_emit<NCH, VSQ>(r[8 + k3], r[8 + 7 - k3], FF::THREADS + FF::CCOLS * k3, xrow, prow, pmode, vrow);
         }
     }
 }
 
 
 void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,
-                 float* P, int pmode, int frames_per_cta) {
+                 float* P, int pmode, int frames_per_cta, float* Vsq) {
     dim3 grid((g.T + frames_per_cta - 1) / frames_per_cta, g.n_items);
+    if (Vsq) {  // X, P and the squared magnitudes of every channel (adaptive)
+        if (nch == 2) k_stft<2, 4, false, true><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta, Vsq);
+        else k_stft<1, 4, false, true><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta, Vsq);
+        return;
+    }
 #define REPET_GO(NCH, MINB) k_stft<NCH, MINB><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, X, P, pmode, frames_per_cta)
     if (pmode == P_MIXDOWN) {  // spectrogram only: X is not written
         if (nch == 2) k_stft<2, 4, true><<<grid, FF::THREADS, 0, st>>>(audio, g, window, tb, nullptr, P, pmode, frames_per_cta);
@@ -1193,9 +1213,90 @@ k_adaptive_model(const float2* __restrict__ X, int T, int nch, const int* __rest
     }
 }
 
+// The same from the squared-magnitude plane Vsq [item][frame][channel][PPITCH] written by k_stft: a thread takes four
+// adjacent bins (one 16-byte load per tap), so a tap costs 4 bytes per bin of L2 traffic instead of 8 -- the kernel
+// runs at the L2 throughput cap (5 taps per frame: ~11 TB/s with the spectra as the source, profiles/r2a).
+template <int N>
+__device__ __forceinline__ void vsq_median_quad(const float* __restrict__ base, size_t stride, float* __restrict__ out) {
+    float v0[N], v1[N], v2[N], v3[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(base + (size_t)s * stride));
+        v0[s] = x.x;
+        v1[s] = x.y;
+        v2[s] = x.z;
+        v3[s] = x.w;
+    }
+    median_select<N>(v0);
+    median_select<N>(v1);
+    median_select<N>(v2);
+    median_select<N>(v3);
+    float4 m;
+    if (N & 1) {
+        m = make_float4(fast_sqrt(v0[(N - 1) / 2]), fast_sqrt(v1[(N - 1) / 2]), fast_sqrt(v2[(N - 1) / 2]), fast_sqrt(v3[(N - 1) / 2]));
+    } else {
+        m = make_float4(0.5f * (fast_sqrt(v0[(N - 1) / 2]) + fast_sqrt(v0[N / 2])), 0.5f * (fast_sqrt(v1[(N - 1) / 2]) + fast_sqrt(v1[N / 2])),
+                        0.5f * (fast_sqrt(v2[(N - 1) / 2]) + fast_sqrt(v2[N / 2])), 0.5f * (fast_sqrt(v3[(N - 1) / 2]) + fast_sqrt(v3[N / 2])));
+    }
+    *reinterpret_cast<float4*>(out) = m;
+}
+template <int N>
+__device__ __forceinline__ float vsq_median_one(const float* __restrict__ base, size_t stride) {
+    float v[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) v[s] = __ldg(base + (size_t)s * stride);
+    median_select<N>(v);
+    return (N & 1) ? fast_sqrt(v[(N - 1) / 2]) : 0.5f * (fast_sqrt(v[(N - 1) / 2]) + fast_sqrt(v[N / 2]));
+}
+
+constexpr int ADAPTIVE_V_MAX = 16;  // filter orders up to 16 take the Vsq kernel
+
+__global__ void __launch_bounds__(128)
+k_adaptive_model_v(const float* __restrict__ Vsq, int T, int nch, const int* __restrict__ frame_period, int order,
+                   float* __restrict__ model) {
+    const int item = blockIdx.y / nch, c = blockIdx.y - item * nch;
+    const int t = threadIdx.x;
+    const int half = (order + 1) / 2;  // ceil(order / 2)
+    const size_t row = (size_t)nch * PPITCH;
+    const float* __restrict__ chan = Vsq + (size_t)item * T * row + (size_t)c * PPITCH;
+    float* __restrict__ mrow = model + ((size_t)item * nch + c) * (size_t)T * PPITCH;
+    const int* __restrict__ fp = frame_period + (size_t)item * T;
+    const int j_begin = blockIdx.x * MODEL_QB, j_end = min(T, j_begin + MODEL_QB);
+    for (int j = j_begin; j < j_end; ++j) {
+        const int p = fp[j];
+        int c_lo = 1 - half, c_hi = order - half;
+        if (p > 0) {
+            c_lo = max(c_lo, -(j / p));
+            c_hi = min(c_hi, (T - 1 - j) / p);
+        } else {
+            c_lo = c_hi = 0;
+        }
+        const int n = c_hi - c_lo + 1;
+        const float* __restrict__ base = chan + (size_t)(j + c_lo * p) * row;
+        const size_t stride = (size_t)max(p, 0) * row;
+        float* __restrict__ out = mrow + (size_t)j * PPITCH;
+        switch (n) {
+#define REPET_CASE(N)                                                                           \
+    case N:                                                                                     \
+        for (int k = 4 * t; k < XPITCH; k += 512) vsq_median_quad<N>(base + k, stride, out + k); \
+        if (t == 0) out[XPITCH] = vsq_median_one<N>(base + XPITCH, stride);                     \
+        break;
+            REPET_CASE(1) REPET_CASE(2) REPET_CASE(3) REPET_CASE(4) REPET_CASE(5) REPET_CASE(6) REPET_CASE(7)
+            REPET_CASE(8) REPET_CASE(9) REPET_CASE(10) REPET_CASE(11) REPET_CASE(12) REPET_CASE(13) REPET_CASE(14)
+            REPET_CASE(15) REPET_CASE(16)
+#undef REPET_CASE
+        }
+    }
+}
+
 void launch_adaptive_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* frame_period,
-                           int order, float* model) {
+                           int order, float* model, const float* Vsq) {
     const int n_groups = (T + MODEL_QB - 1) / MODEL_QB;
+    if (Vsq && order <= ADAPTIVE_V_MAX) {
+        dim3 grid(n_groups, n_items * nch);
+        k_adaptive_model_v<<<grid, 128, 0, st>>>(Vsq, T, nch, frame_period, order, model);
+        return;
+    }
     dim3 grid(n_groups + 1, n_items * nch);
     k_adaptive_model<<<grid, 128, 0, st>>>(X, T, nch, frame_period, order, model, n_groups);
 }

@@ -24,6 +24,7 @@ struct repet_tuning {
     int simgemm_tc = 2;      // similarity fast pass: 2 = tcgen05 3xTF32 split, 1 = tcgen05 single TF32, 0 = fp32 CUDA cores
     int copy_chunk_mb = 128; // host-buffer entry points: megabytes per copy slot (pipeline granularity)
     int sim_frames64 = 1;    // similarity operand from the float64 front end (k_frames64); 0 = from k_stft's fp32 magnitudes
+    int adaptive_vsq = 1;    // adaptive: k_stft also writes |X|^2 planes and the per-frame median gathers those
     int simgemm_bn = 256;    // tile width of the split similarity GEMM: 256 (128 x 256 tiles) or 128 (square tiles)
     int topk_force_exact = 0;  // test knob: every column of REPET-SIM goes through the exact float64 fallback
 };
@@ -96,8 +97,9 @@ using Tuning = ::repet_tuning;
 static Tuning& g_tuning = ::g_repet_tuning;
 
 // k_stft: audio -> X (half spectra, both channels) [+ P = (mean_c |X|)^2 or mean_c |X|]
+// Vsq (optional): also |X_c|^2 of every channel, [item][frame][channel][PPITCH]
 void launch_stft(cudaStream_t st, const float* audio, Geom g, int nch, const float* window, FftTables tb, float2* X,
-                 float* P, int pmode, int frames_per_cta);
+                 float* P, int pmode, int frames_per_cta, float* Vsq = nullptr);
 
 // k_beat: P rows [t_first, t_first + t_len) of every item (zero outside [0, T)) -> partial PSD sums
 // psd_part[item][part][2048]
@@ -140,8 +142,9 @@ void launch_mask_only(cudaStream_t st, const float2* X, int n_items, int T, int 
 // adaptive: per-frame periods from per-segment periods (quirk Q3), per-frame median model
 void launch_expand_periods(cudaStream_t st, const int* seg_period, int n_items, int n_seg, int T, int step, int lag_lo,
                            int* frame_period);
+// Vsq (optional, from launch_stft): the taps are gathered from the 4-byte squared magnitudes instead of the spectra
 void launch_adaptive_model(cudaStream_t st, const float2* X, int n_items, int T, int nch, const int* frame_period,
-                           int order, float* model);
+                           int order, float* model, const float* Vsq = nullptr);
 // extended: triangular cross-fade of the separated segments
 void launch_xfade(cudaStream_t st, const float* seg_main, const float* seg_last, int n_clips, int n_seg, int seg_len,
                   int last_len, int step, int nch, long long S, float* out);

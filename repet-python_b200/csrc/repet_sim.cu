@@ -315,9 +315,22 @@ __device__ __forceinline__ double warp_dot64(const double* __restrict__ a, const
 // With tau = 0 this is the reference's rule verbatim (strict >, windows clipped at the ends,
 // NaN never a maximum: quirk Q7).
 // ------------------------------------------------------------------------------------------
-constexpr int TOPK_THREADS = 512;
-constexpr int TOPK_CAP = 2048;       // candidates per column held in shared memory
-constexpr int TOPK_CHUNK = 4096;     // elements of the fast row resident at a time (3 arrays); 88 KB -> 2 CTAs/SM
+// CTA shape, measured on the 10-minute track (scripts/gpu_topk_sweep.sh, profiles/r2e_topk_sweep.txt): the kernel is
+// a chain of short phases separated by barriers (ncu: barrier stalls 9.4 per issue at 512 threads, 2 CTAs / SM), so
+// smaller CTAs with a smaller shared-memory footprint (38 KB -> 5 CTAs / SM) hide them: 4.82 -> 3.35 ms.  Columns
+// with more than TOPK_CAP candidates go to k_topk_exact.
+#ifndef REPET_TOPK_THREADS
+#define REPET_TOPK_THREADS 256
+#endif
+#ifndef REPET_TOPK_CAP
+#define REPET_TOPK_CAP 768
+#endif
+#ifndef REPET_TOPK_CHUNK
+#define REPET_TOPK_CHUNK 1536
+#endif
+constexpr int TOPK_THREADS = REPET_TOPK_THREADS;
+constexpr int TOPK_CAP = REPET_TOPK_CAP;       // candidates per column held in shared memory
+constexpr int TOPK_CHUNK = REPET_TOPK_CHUNK;   // elements of the fast row resident at a time (3 arrays)
 constexpr int TOPK_BINS = 512;       // histogram of fast values over [-1, 1) for the top-`number` cut
 __device__ __forceinline__ int topk_bin(float v) {
     return min(TOPK_BINS - 1, max(0, (int)floorf((v + 1.f) * (TOPK_BINS / 2.f))));

@@ -215,9 +215,10 @@ def test_exact_fallback_gives_the_reference_lists(repet):
 
 def test_stationary_track_overflows_the_candidate_budget_and_still_matches(repet):
     """A steady chord with a little noise: every frame resembles every other to within 2 tau, so each column of the
-    similarity matrix proposes T > 2048 candidates -- the data-dependent case that used to be refused.  Lists must
+    similarity matrix proposes ~T candidates, far over the budget k_topk holds in shared memory -- the data-dependent
+    case that used to be refused.  Lists must
     equal the oracle's (the exact similarities differ by ~1e-9, far above float64 rounding)."""
-    seconds = 56  # T = 2413 frames > the 2048-candidate budget
+    seconds = 56  # T = 2413 frames: ~2200 candidates per column
     n = seconds * FS
     time = np.arange(n) / FS
     rng = np.random.default_rng(77)
