@@ -594,7 +594,7 @@ k_gen_gram(const double* __restrict__ An, long long T, int F, double* __restrict
 // `kept` is scratch for n ints.  slot_frame (optional) maps a position to the frame index written out (simonline).
 __device__ void gen_localmaxima(const double* __restrict__ v, int n, double thr, int d, int number, int* __restrict__ kept,
                                 int* __restrict__ s_count, int* __restrict__ idx_out, int* __restrict__ cnt_out, int j_online,
-                                int B_online) {
+                                int B_online, int base_online = 0) {
     if (threadIdx.x == 0) *s_count = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -617,9 +617,9 @@ __device__ void gen_localmaxima(const double* __restrict__ v, int n, double thr,
         }
         if (rank < number) {
             int out = i;
-            if (B_online > 0) {  // ring slot -> frame index (repet.py:837, 852; quirk Q6)
+            if (B_online > 0) {  // ring slot -> frame index (repet.py:837, 852; quirk Q6); j_online carries the base
                 const int j0 = j_online % B_online;
-                out = i <= j0 ? j_online - (j0 - i) : j_online - (j0 - i) - B_online;
+                out = (i <= j0 ? j_online - (j0 - i) : j_online - (j0 - i) - B_online) - base_online;
             }
             idx_out[rank] = out;
         }
@@ -640,28 +640,35 @@ k_gen_indices(const double* __restrict__ S, int T, double thr, int d, int number
     gen_localmaxima(v, T, thr, d, number, kept, &s_count, idx + (long long)c * number, cnt + c, 0, 0);
 }
 // online REPET-SIM: frame j >= B-1 against the B frames of its ring buffer in SLOT order (repet.py:834-866, quirk Q6)
+// Rows are frames base .. base + T - 1 of a longer stream (base = repet_params.online_frame_base; 0 for a whole
+// signal): the ring slot of a frame is its ABSOLUTE index mod B, and slots whose frame lies before the window hold
+// no data (-inf: never a maximum), exactly as in the fast path's k_online_select.
 __global__ void __launch_bounds__(256)
-k_gen_online(const double* __restrict__ An, int T, int F, int B, double thr, int d, int number, int* __restrict__ idx,
-             int* __restrict__ cnt) {
+k_gen_online(const double* __restrict__ An, int T, int F, int B, int base, int row_first, double thr, int d, int number,
+             int* __restrict__ idx, int* __restrict__ cnt) {
     extern __shared__ __align__(16) unsigned char gsm[];
     double* v = reinterpret_cast<double*>(gsm);       // [B] similarity by slot
     int* kept = reinterpret_cast<int*>(v + B);        // [B]
     __shared__ int s_count;
-    const int j = blockIdx.x + (B - 1);
+    const int j = blockIdx.x + row_first;             // row inside the window
     if (j >= T) return;
-    const int j0 = j % B;
+    const int ja = j + base;                          // absolute frame index
+    const int j0 = ja % B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const double* __restrict__ a = An + (long long)j * F;
     for (int b = warp; b < B; b += nwarp) {
-        const int u = b <= j0 ? j - (j0 - b) : j - (j0 - b) - B;
-        const double* __restrict__ x = An + (long long)u * F;
-        double acc = 0.0;
-        for (int f = lane; f < F; f += 32) acc = fma(a[f], x[f], acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const int u = (b <= j0 ? ja - (j0 - b) : ja - (j0 - b) - B) - base;  // row of the frame in slot b
+        double acc = -INFINITY;
+        if (u >= 0) {
+            const double* __restrict__ x = An + (long long)u * F;
+            acc = 0.0;
+            for (int f = lane; f < F; f += 32) acc = fma(a[f], x[f], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
         if (lane == 0) v[b] = acc;
     }
     __syncthreads();
-    gen_localmaxima(v, B, thr, d, number, kept, &s_count, idx + (long long)j * number, cnt + j, j, B);
+    gen_localmaxima(v, B, thr, d, number, kept, &s_count, idx + (long long)j * number, cnt + j, ja, B, base);
 }
 
 // median of n values fetched by `fetch(s)`: insertion sort in local memory up to GEN_SORT_MAX, exact rank selection
@@ -841,11 +848,14 @@ int gen_run(repet_handle* h, int method, const double* d_audio, long long S, int
     if (online) {
         const int B = p->buffer_frames;
         if (B < 1) return fail(h, REPET_E_INVALID_ARG, "buffer_length must cover at least one frame");
-        if (S < N || (long long)(B - 2) * H + N > S)  // the reference's warm-up loop fails to broadcast (repet.py:801-804)
+        if (p->online_frame_base < 0) return fail(h, REPET_E_INVALID_ARG, "online_frame_base must not be negative");
+        // the reference's warm-up loop fails to broadcast (repet.py:801-804); a window of a longer stream
+        // (online_frame_base > 0) has had its warm-up earlier
+        if (S < N || (p->online_frame_base == 0 && (long long)(B - 2) * H + N > S))
             return fail(h, REPET_E_INVALID_ARG, "operands could not be broadcast together (signal shorter than the buffer)");
         T = (S - N + H - 1) / H + 1;  // repet.py:781
         pad = 0;
-        first_frame = B - 1;
+        first_frame = std::max(0, B - 1 - p->online_frame_base);
     } else {
         T = (S + H - 1) / H + 1;  // repet.py:1018-1028 with N = 2H
         pad = N / 2;
@@ -907,9 +917,10 @@ int gen_run(repet_handle* h, int method, const double* d_audio, long long S, int
             const size_t smem = (size_t)B * 12 + 16;
             if (smem > 200 * 1024) return fail(h, REPET_E_UNSUPPORTED, "buffer_length too long for the general online selection");
             if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gen_online, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (T > B - 1)
-                k_gen_online<<<(unsigned)(T - (B - 1)), 256, smem, st>>>(An, (int)T, F, B, p->similarity_threshold,
-                                                                        p->similarity_distance, number, idx, cnt);
+            if (T > first_frame)
+                k_gen_online<<<(unsigned)(T - first_frame), 256, smem, st>>>(An, (int)T, F, B, p->online_frame_base, first_frame,
+                                                                            p->similarity_threshold, p->similarity_distance,
+                                                                            number, idx, cnt);
         } else {
             double* Sm = pool.get<double>((size_t)T * T);
             if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory for the similarity matrix");

@@ -210,13 +210,32 @@ def spectrogram_db(audio_spectrogram):
     return 20 * np.log10(audio_spectrogram)
 
 
-class SimOnline(_host.SimOnlineStream):
+class SimOnline:
     """Streaming front end of the online REPET-SIM: `SimOnline(sampling_frequency, number_channels)`, then
     `process(block)` per block of samples and `flush()` at the end; the concatenated outputs equal
-    `repet.simonline` on the whole signal.  The module tunables are read at construction."""
+    `repet.simonline` on the whole signal.  The module tunables are read at construction.
+
+    Streams the fast kernels cover (window lengths up to 2048, one or two channels) run on the stateful C stream
+    (sample history resident on the device); other sampling rates and channel counts use the same bookkeeping on the
+    host over the general float64 device path."""
 
     def __init__(self, sampling_frequency, number_channels):
-        super().__init__(sampling_frequency, number_channels, _tunables())
+        tunables = _tunables()
+        params, _ = _host.derive_params(sampling_frequency, tunables, "simonline")
+        if _host.needs_general_path(params, int(number_channels)):
+            self._impl = _host.SimOnlineStreamHost(sampling_frequency, number_channels, tunables)
+        else:
+            self._impl = _host.SimOnlineStream(sampling_frequency, number_channels, tunables)
+
+    def process(self, block):
+        return self._impl.process(block)
+
+    def flush(self):
+        return self._impl.flush()
+
+    def close(self):
+        if hasattr(self._impl, "close"):
+            self._impl.close()
 
 
 def wavread(audio_file):

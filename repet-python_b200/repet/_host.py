@@ -1159,8 +1159,17 @@ class SimOnlineStreamHost:
         params = RepetParams()
         ctypes.memmove(ctypes.byref(params), ctypes.byref(self.params), ctypes.sizeof(RepetParams))
         params.online_frame_base = int(first_frame)
-        self.handle.ensure_window(params.window_length)
         out = np.empty_like(window)
+        if needs_general_path(params, self.channels):
+            hamming = np.ascontiguousarray(hamming_window(params.window_length), dtype=np.float64)
+            self.handle.check(
+                self.handle.lib.repet_general_f64(
+                    self.handle.h, METHODS["simonline"], _ptr(window), window.shape[0], self.channels, ctypes.byref(params),
+                    _ptr(hamming), _ptr(out), None, 0
+                )
+            )
+            return out
+        self.handle.ensure_window(params.window_length)
         self.handle.check(
             self.handle.lib.repet_simonline_f64(
                 self.handle.h, _ptr(window), window.shape[0], self.channels, ctypes.byref(params), _ptr(out), None, 0

@@ -198,3 +198,19 @@ def test_general_batch_and_separate(repet):
     y_ref = oracle.adaptive(audio[0].T.astype(np.float64), FS)
     _signal_close(parts["background"], y_ref, "3-channel separate")
     assert parts["background_spectrogram"].shape == (1025, parts["audio_spectrogram"].shape[1])
+
+
+def test_stream_at_general_shapes_matches_the_whole_signal_call(repet):
+    """repet.SimOnline on a three-channel stream and on a 96 kHz stream: the host-side bookkeeping over windows of
+    the general float64 path (ring slots of the whole stream through online_frame_base, quirk Q6)."""
+    for fs, channels, seconds in ((FS, 3, 14), (96000, 2, 13)):
+        spec = dict(kind="synth", fs=fs, index=970 + channels, samples=seconds * fs + 321, channels=channels)
+        x = make_golden.case_input(spec)
+        whole = repet.simonline(x, fs)
+        stream = repet.SimOnline(fs, channels)
+        pieces = [stream.process(x[k : k + fs]) for k in range(0, len(x), fs)]
+        pieces.append(stream.flush())
+        streamed = np.concatenate(pieces)
+        assert streamed.shape == whole.shape
+        _signal_close(streamed, whole, "stream %d Hz %d ch" % (fs, channels), tol=1e-12)
+        _signal_close(whole, oracle.simonline(x, fs), "whole vs oracle %d Hz %d ch" % (fs, channels))
