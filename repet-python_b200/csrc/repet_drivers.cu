@@ -329,7 +329,8 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
         const bool frames64 = g_tuning.sim_frames64 != 0;
         {
             Timed timed(h, REPET_K_STFT);
-            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, frames64 ? nullptr : V, P_MAGNITUDE, K);
+            // long lists gather squared magnitudes: k_stft writes that plane itself (round 1 ran a separate k_sqmag pass)
+            launch_stft(st, audio, geom, nch, window_of(h), tables(h), X, frames64 ? nullptr : V, P_MAGNITUDE, K, Vsq);
         }
         {
             Timed timed(h, REPET_K_NORMALIZE);
@@ -364,8 +365,7 @@ int run_sim(repet_handle* h, const Plan& plan, const float* audio, int n_clips, 
                 return fail(h, REPET_E_UNSUPPORTED, "track too long for the in-shared-memory similarity row");
         }
         {
-            Timed timed(h, REPET_K_MODEL, Vsq ? 4 : 2);  // [k_sqmag,] k_simmodel, [k_simmodel_large,] k_simmodel_nyquist
-            if (Vsq) launch_sqmag(st, X, (long long)g * T * nch, Vsq);
+            Timed timed(h, REPET_K_MODEL, Vsq ? 3 : 2);  // k_simmodel, [k_simmodel_large,] k_simmodel_nyquist
             if (launch_simmodel(st, X, Vsq, g, T, nch, idx, cnt, plan.number, geom.first_frame, model))
                 return fail(h, REPET_E_UNSUPPORTED, "similarity_number too large for the shared-memory median");
         }

@@ -161,13 +161,19 @@ def sim_batch(audio_signals, sampling_frequency):
     return _host.driver_batch("sim", audio_signals, sampling_frequency, _tunables())
 
 
-def extended(audio_signal, sampling_frequency):
-    """Compute REPET extended (repet.py:205-419)."""
+def extended(audio_signal, sampling_frequency, devices=None):
+    """Compute REPET extended (repet.py:205-419).  `devices` (beyond the reference): split ONE long track by time
+    block over several GPUs (whole segments per block, junctions cross-faded as the reference does)."""
+    if devices is not None:
+        return _host.sharded_track("extended", audio_signal, sampling_frequency, _tunables(), devices)
     return _host.extended_f64(audio_signal, sampling_frequency, _tunables())
 
 
-def adaptive(audio_signal, sampling_frequency):
-    """Compute the adaptive REPET (repet.py:422-568)."""
+def adaptive(audio_signal, sampling_frequency, devices=None):
+    """Compute the adaptive REPET (repet.py:422-568).  `devices`: ONE long track by time block over several GPUs
+    (blocks cut on the beat-spectrogram grid, separated with a halo)."""
+    if devices is not None:
+        return _host.sharded_track("adaptive", audio_signal, sampling_frequency, _tunables(), devices)
     return _host.adaptive_f64(audio_signal, sampling_frequency, _tunables())
 
 
@@ -176,8 +182,11 @@ def sim(audio_signal, sampling_frequency):
     return _host.sim_f64(audio_signal, sampling_frequency, _tunables())
 
 
-def simonline(audio_signal, sampling_frequency):
-    """Compute the online REPET-SIM (repet.py:712-911)."""
+def simonline(audio_signal, sampling_frequency, devices=None):
+    """Compute the online REPET-SIM (repet.py:712-911).  `devices`: ONE long track by time block over several GPUs
+    (every block replays the similarity history of its first frames)."""
+    if devices is not None:
+        return _host.sharded_track("simonline", audio_signal, sampling_frequency, _tunables(), devices)
     return _host.simonline_f64(audio_signal, sampling_frequency, _tunables())
 
 

@@ -903,6 +903,155 @@ def _separate_batch_general(driver, audio, in_code, out_code, sampling_frequency
     return result, np.stack(integers) if integers else np.zeros((0, 1), np.int32)
 
 
+# ------------------------------------------------------------------------------------------
+# one long track over several GPUs, by time block ("finer partitions")
+# ------------------------------------------------------------------------------------------
+def _run_shards(jobs, devices):
+    """jobs: list of callables f(handle) -> result, shard k runs on devices[k % len(devices)]; one host thread per
+    DISTINCT device (a handle is not re-entrant), shards of a device in order.  Returns the results in job order."""
+    devices = [int(d) for d in devices]
+    if not devices:
+        raise ValueError("devices must name at least one GPU")
+    results = [None] * len(jobs)
+    errors = []
+    by_device = {}
+    for k in range(len(jobs)):
+        by_device.setdefault(devices[k % len(devices)], []).append(k)
+    handles = {d: get_handle(d) for d in by_device}
+
+    def worker(device):
+        try:
+            for k in by_device[device]:
+                results[k] = jobs[k](handles[device])
+        except BaseException as exc:  # re-raised on the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in by_device]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def track_time_blocks(driver, number_samples, params, number_shards):
+    """Sample ranges [a, b) that split ONE track of `driver` into `number_shards` time blocks whose separate
+    separations can be merged into exactly the whole-track result (pure host logic, tested on CPU):
+
+    extended   cuts at multiples of the segment step: block k holds whole 10 s segments, the last segment of a block
+               has the regular length (only the track's last segment absorbs the remainder, repet.py:320-322)
+    adaptive   cuts at multiples of the beat-spectrogram step in samples: the segment grid (repet.py:1194) is anchored
+               at frame 0 of every block exactly as in the whole track
+    simonline  cuts at multiples of the hop: every block replays its similarity history (buffer_frames - 1 frames)
+               through online_frame_base
+    Returns a list of (a, b); fewer than number_shards entries when the track is too short to cut."""
+    S, K = int(number_samples), max(1, int(number_shards))
+    if driver == "extended":
+        seg_len, step = params.segment_length, params.segment_step
+        if S < seg_len + step:
+            return [(0, S)]
+        n_seg = 1 + (S - seg_len) // step
+        K = min(K, n_seg)
+        cuts = [0]
+        for k in range(1, K):
+            m = (n_seg * k) // K  # first segment of block k
+            if m * step > cuts[-1]:
+                cuts.append(m * step)
+        return [(a, b) for a, b in zip(cuts, cuts[1:] + [S])]
+    if driver == "adaptive":
+        unit = params.segment_step * params.step_length
+    elif driver == "simonline":
+        unit = params.step_length
+    else:
+        raise ValueError("time-block sharding applies to extended, adaptive and simonline")
+    n_units = S // unit
+    K = min(K, max(1, n_units))
+    if driver == "simonline":
+        # the first block must get through the reference's warm-up on its own (repet.py:794-810)
+        K = min(K, max(1, S // ((params.buffer_frames + 1) * unit)))
+    cuts = sorted({(n_units * k) // K * unit for k in range(K)})
+    return [(a, b) for a, b in zip(cuts, cuts[1:] + [S])]
+
+
+def sharded_track(driver, audio_signal, sampling_frequency, tunables, devices):
+    """ONE long track split by time block over several GPUs (one handle and one host thread per GPU; more blocks
+    than GPUs run in turn).  The merged output equals the single-call result: to rounding for `extended` (the
+    junction cross-fade is applied in float64 on the host, repet.py:398-409) and `adaptive` (every block is
+    separated with a halo that covers the beat-spectrogram segments and the median taps of its frames, and only
+    its own samples are kept), bit for bit for `simonline` (each block replays its similarity history)."""
+    x = np.ascontiguousarray(audio_signal, dtype=np.float64)
+    number_samples, number_channels = x.shape
+    params, _ = derive_params(sampling_frequency, tunables, driver)
+    blocks = track_time_blocks(driver, number_samples, params, len(list(devices)))
+    if len(blocks) == 1:
+        return {"extended": extended_f64, "adaptive": adaptive_f64, "simonline": simonline_f64}[driver](
+            x, sampling_frequency, tunables)
+    out = np.empty_like(x)
+    if driver == "extended":
+        seg_len, step = params.segment_length, params.segment_step
+        overlap = seg_len - step
+        # block k = samples [a_k, b_k + overlap): its last segment reaches `overlap` samples into the next block
+        jobs = [(lambda h, a=a, b=b: extended_f64(x[a : min(b + overlap, number_samples)], sampling_frequency, tunables,
+                                                  handle=h)) for a, b in blocks]
+        parts = _run_shards(jobs, devices)
+        import scipy.signal.windows
+
+        window = scipy.signal.windows.triang(2 * overlap)  # repet.py:284
+        for (a, b), y in zip(blocks, parts):
+            if a == 0:
+                out[: len(y)] = y
+            else:
+                # the reference's in-place step for the block's first segment (repet.py:398-409): what is already
+                # there fades out, the new segment fades in, the rest is the block's own
+                out[a : a + overlap] = out[a : a + overlap] * window[overlap:, None] + y[:overlap] * window[:overlap, None]
+                out[a + overlap : a + len(y)] = y[overlap:]
+        return out
+    if driver == "adaptive":
+        unit = params.segment_step * params.step_length
+        halo = 3 * unit  # beat segments reach 1 step, the 5 median taps 2 periods (< 2 steps) beyond a frame
+        jobs = []
+        for a, b in blocks:
+            lo, hi = max(0, a - halo), min(number_samples, b + halo)
+            jobs.append(lambda h, lo=lo, hi=hi, a=a, b=b: adaptive_f64(x[lo:hi], sampling_frequency, tunables, handle=h)[a - lo : b - lo])
+        for (a, b), y in zip(blocks, _run_shards(jobs, devices)):
+            out[a:b] = y
+        return out
+    # simonline: a block is a window of the stream -- its samples plus the history its first frames look back on
+    N, H, B = params.window_length, params.step_length, params.buffer_frames
+    if (B - 2) * H + N > number_samples:
+        raise ValueError("operands could not be broadcast together (signal shorter than the buffer)")
+
+    def online_block(h, a, b):
+        first_block = a // H
+        first_needed = max(0, first_block - 1)  # output hop b mixes frames b - 1 and b
+        first_frame = max(0, first_needed - (B - 1))
+        lo = first_frame * H
+        # frames that touch [a, b): up to the one starting below b; the window must hold whole frames
+        last_frame = min((b - 1) // H, max(0, -(-(number_samples - N) // H)))
+        hi = min(number_samples, last_frame * H + N)
+        window = np.ascontiguousarray(x[lo:hi])
+        p = RepetParams()
+        ctypes.memmove(ctypes.byref(p), ctypes.byref(params), ctypes.sizeof(RepetParams))
+        p.online_frame_base = int(first_frame)
+        y = np.empty_like(window)
+        if needs_general_path(p, number_channels):
+            hamming = np.ascontiguousarray(hamming_window(N), dtype=np.float64)
+            h.check(h.lib.repet_general_f64(h.h, METHODS["simonline"], _ptr(window), window.shape[0], number_channels,
+                                            ctypes.byref(p), _ptr(hamming), _ptr(y), None, 0))
+        else:
+            h.ensure_window(N)
+            h.check(h.lib.repet_simonline_f64(h.h, _ptr(window), window.shape[0], number_channels, ctypes.byref(p), _ptr(y),
+                                              None, 0))
+        return y[a - lo : b - lo]
+
+    jobs = [(lambda h, a=a, b=b: online_block(h, a, b)) for a, b in blocks]
+    for (a, b), y in zip(blocks, _run_shards(jobs, devices)):
+        out[a:b] = y
+    return out
+
+
 def ragged_groups(shapes):
     """Group clip indices by (channels, samples): clips of equal shape go through one batch call.  Pure host
     logic (the groups are returned in order of first appearance, indices ascending inside a group)."""

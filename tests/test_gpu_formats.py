@@ -145,3 +145,18 @@ def test_simonline_with_a_ring_longer_than_shared_memory(repet):
     first = det["first_frame"]
     assert all(np.array_equal(a, b) for a, b in zip(lists[first:], det["indices"]))
     assert float(np.max(np.abs(y - y_ref))) <= 1e-4 * float(np.max(np.abs(y_ref)))
+
+
+def test_one_long_track_split_by_time_block(repet):
+    """SURVEY.md 8(e) "finer partitions": ONE track cut into time blocks (one per listed device; a repeated device
+    runs its blocks in turn, so this also runs on a 1-GPU box) and merged must equal the single-call result."""
+    x = repet_synth.make_clip(950, 47 * FS + 777, redraw_seconds=(10, 15)).T.astype(np.float64)
+    devices = [0, 0, 0] if repet._host.device_count() < 3 else [0, 1, 2]
+    for name, tol in (("extended", 1e-6), ("adaptive", 1e-6), ("simonline", 0.0)):
+        whole = getattr(repet, name)(x, FS)
+        split = getattr(repet, name)(x, FS, devices=devices)
+        assert split.shape == whole.shape
+        err = float(np.max(np.abs(split - whole))) / float(np.max(np.abs(whole)))
+        assert err <= tol, "%s: %.3e" % (name, err)
+    params, _ = repet._host.derive_params(FS, repet._tunables(), "extended")
+    assert len(repet._host.track_time_blocks("extended", len(x), params, 3)) == 3

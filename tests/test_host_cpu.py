@@ -226,3 +226,29 @@ def test_param_cache_accepts_array_tunables():
     odd = dict(base, period_range=[[1], [10]])  # nested: still derivable, cached or not
     p_odd, _ = _host.derive_params(44100, odd)
     assert (p_odd.period_lo, p_odd.period_hi) == (p_list.period_lo, p_list.period_hi)
+
+
+def test_time_blocks_of_one_track_tile_it_on_the_right_grid():
+    """repet.extended / adaptive / simonline(devices=...): the cuts of ONE long track (pure host logic)."""
+    from repet import _host
+
+    tun = dict(cutoff_frequency=100, period_range=[1, 10], segment_length=10, segment_step=5, filter_order=5,
+               similarity_threshold=0, similarity_distance=1, similarity_number=100, buffer_length=10)
+    fs = 44100
+    for driver, samples in (("extended", 3600 * fs), ("extended", 26 * fs), ("extended", 14 * fs), ("adaptive", 600 * fs),
+                            ("adaptive", 100000), ("simonline", 155038 * 1024 + 2048), ("simonline", 12 * fs)):
+        params, _ = _host.derive_params(fs, tun, driver)
+        for shards in (1, 2, 3, 8):
+            blocks = _host.track_time_blocks(driver, samples, params, shards)
+            assert 1 <= len(blocks) <= shards
+            assert blocks[0][0] == 0 and blocks[-1][1] == samples
+            assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(blocks, blocks[1:]))
+            unit = {"extended": params.segment_step, "adaptive": params.segment_step * params.step_length,
+                    "simonline": params.step_length}[driver]
+            assert all(a % unit == 0 for a, _ in blocks)
+    params, _ = _host.derive_params(fs, tun, "extended")
+    assert _host.track_time_blocks("extended", 14 * fs, params, 4) == [(0, 14 * fs)]  # a single segment cannot be cut
+    params, _ = _host.derive_params(fs, tun, "simonline")
+    assert len(_host.track_time_blocks("simonline", 12 * fs, params, 4)) == 1  # the first block needs the warm-up
+    with pytest.raises(ValueError):
+        _host.track_time_blocks("sim", 10 * fs, params, 2)
