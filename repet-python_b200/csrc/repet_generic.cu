@@ -433,13 +433,31 @@ namespace {
 
 enum { GEN_ORIGINAL = 0, GEN_EXTENDED = 1, GEN_ADAPTIVE = 2, GEN_SIM = 3, GEN_SIMONLINE = 4 };
 
-struct Pool {  // device allocations of one call, released together
+// Device allocations of one call, released together.  Stream-ordered (cudaMallocAsync): the driver's memory pool
+// keeps up to 8 GB of freed blocks, so the per-segment calls of `extended` and repeated calls reuse them instead of
+// paying cudaMalloc / cudaFree (which synchronise the device) every time.
+struct Pool {
+    cudaStream_t st;
     std::vector<void*> ptrs;
     bool ok = true;
+    explicit Pool(cudaStream_t stream) : st(stream) {
+        static bool configured[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = (uint64_t)8 << 30;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
+            configured[dev & 63] = true;
+        }
+    }
     template <typename T>
     T* get(size_t n) {
         void* p = nullptr;
-        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+        if (cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st) != cudaSuccess) {
             (void)cudaGetLastError();
             ok = false;
             return nullptr;
@@ -450,13 +468,13 @@ struct Pool {  // device allocations of one call, released together
     void release(void* p) {
         for (size_t i = 0; i < ptrs.size(); ++i)
             if (ptrs[i] == p) {
-                cudaFree(p);
+                cudaFreeAsync(p, st);
                 ptrs.erase(ptrs.begin() + i);
                 return;
             }
     }
     ~Pool() {
-        for (void* p : ptrs) cudaFree(p);
+        for (void* p : ptrs) cudaFreeAsync(p, st);
     }
 };
 
@@ -713,12 +731,27 @@ __device__ double gen_median(int n, Fetch fetch) {
     return 0.5 * (v_lo + v_hi);
 }
 
+// the repeating segment of _mask (repet.py:1398-1438): model[c][q][f] = median over s of V[c][q + s p][f], with r or
+// r - 1 values per phase (quirk Q9) -- one median per (channel, phase, bin), shared by every frame of that phase
+__global__ void k_gen_period_model(const double* __restrict__ V, int C, long long T, int F, int period,
+                                   double* __restrict__ model) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)C * period * F) return;
+    const int f = (int)(gid % F);
+    const long long q = (gid / F) % period;
+    const int c = (int)(gid / ((long long)F * period));
+    const double* __restrict__ Vc = V + (long long)c * T * F;
+    const long long r = (T + period - 1) / period;
+    const int n = q >= T ? 0 : (int)(q < T - (r - 1) * period ? r : r - 1);
+    model[gid] = gen_median(n, [&](int s) { return Vc[(q + (long long)s * period) * F + f]; });
+}
+
 // repeating model + soft mask + high-pass + mirror + apply, in place on X (repet.py:1398-1456, 1474-1506, 1529-1543,
 // 185-197).  mode 0: period-strided frames of a phase (quirk Q9); 1: the in-range frames t + c p_t; 2: listed frames.
 __global__ void k_gen_mask_apply(double2* __restrict__ X, const double* __restrict__ V, int C, long long T, int N, int F,
-                                 int mode, int period, const int* __restrict__ frame_period, int order,
-                                 const int* __restrict__ idx, const int* __restrict__ cnt, int number, int first_frame,
-                                 int cutoff) {
+                                 int mode, int period, const double* __restrict__ period_model,
+                                 const int* __restrict__ frame_period, int order, const int* __restrict__ idx,
+                                 const int* __restrict__ cnt, int number, int first_frame, int cutoff) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)C * T * F) return;
     const int f = (int)(gid % F);
@@ -728,11 +761,7 @@ __global__ void k_gen_mask_apply(double2* __restrict__ X, const double* __restri
     const double* __restrict__ Vc = V + (long long)c * T * F;
     double model;
     if (mode == 0) {
-        const int p = period;
-        const long long r = (T + p - 1) / p;
-        const long long q = t % p;
-        const int n = (int)(q < T - (r - 1) * p ? r : r - 1);
-        model = gen_median(n, [&](int s) { return Vc[(q + (long long)s * p) * F + f]; });
+        model = period_model[((long long)c * period + t % period) * F + f];
     } else if (mode == 1) {
         const int p = frame_period[t];
         const int half = (order + 1) / 2;
@@ -840,7 +869,7 @@ int gen_beat(repet_handle* h, Pool& pool, const GenShape& g, const double* Vm, l
 int gen_run(repet_handle* h, int method, const double* d_audio, long long S, int ld, const GenShape& g,
             const repet_params* p, double* d_out, int* d_ints) {
     cudaStream_t st = h->stream;
-    Pool pool;
+    Pool pool(st);
     const int N = g.N, H = g.H, F = g.F, C = g.C;
     const bool online = method == GEN_SIMONLINE;
     long long T;
@@ -936,9 +965,15 @@ int gen_run(repet_handle* h, int method, const double* d_audio, long long S, int
     } else {
         return fail(h, REPET_E_INVALID_ARG, "unknown method");
     }
-    k_gen_mask_apply<<<blocks_for((long long)C * T * F), 256, 0, st>>>(X, V, C, T, N, F, mode, period_host, frame_period,
-                                                                      p->filter_order, idx, cnt, p->similarity_number,
-                                                                      first_frame, p->cutoff_bins);
+    double* period_model = nullptr;
+    if (mode == 0) {
+        period_model = pool.get<double>((size_t)C * period_host * F);
+        if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+        k_gen_period_model<<<blocks_for((long long)C * period_host * F), 256, 0, st>>>(V, C, T, F, period_host, period_model);
+    }
+    k_gen_mask_apply<<<blocks_for((long long)C * T * F), 256, 0, st>>>(X, V, C, T, N, F, mode, period_host, period_model,
+                                                                      frame_period, p->filter_order, idx, cnt,
+                                                                      p->similarity_number, first_frame, p->cutoff_bins);
     fft_pow2(st, X, tmp, N, (long long)C * T, true);
     k_gen_overlap_add<<<blocks_for(S * C), 256, 0, st>>>(X, C, T, N, H, online ? 0 : N - H, first_frame, S,
                                                         1.0 / ((double)N * g.gain), d_out, ld);
@@ -964,7 +999,7 @@ int repet_general_f64(repet_handle* h, int method, const double* audio, int64_t 
     if (method < GEN_ORIGINAL || method > GEN_SIMONLINE) return fail(h, REPET_E_INVALID_ARG, "unknown method");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    Pool pool;
+    Pool pool(st);
     const long long S = n_samples;
     const int C = n_channels;
     const long long need = repet_ints_per_clip(method, p, n_samples);

@@ -133,6 +133,46 @@ def separate_batch(audio_signals, sampling_frequency, method="original", in_form
                                 out_format=out_format, out=out, devices=devices)
 
 
+def separate_files(input_files, output_files, method="original", devices=None):
+    """
+    WAVE files in, WAVE files out: the steps either side of the separation in the reference's usage (wavread ->
+    method -> wavwrite, README.md:56-68) with the samples never leaving their 16-bit form on the host.
+
+    int16 files go to the device as int16 PCM (normalised by 2^15 there, as repet.wavread does, repet.py:929) and come
+    back as int16 (round(y * 2^15), saturated); files of equal length, channel count and sampling rate share one
+    batch call (`devices` shards each batch over several GPUs).  Files in another sample format are read by
+    `wavread`, separated through the float64 entry point and written back as float64 by `wavwrite`, exactly as the
+    reference's own example does.  Returns the list of integer outputs (periods or lists) per file.
+    """
+    import scipy.io.wavfile
+
+    input_files, output_files = list(input_files), list(output_files)
+    if len(input_files) != len(output_files):
+        raise ValueError("one output file per input file expected")
+    loaded = [scipy.io.wavfile.read(path) for path in input_files]
+    integers = [None] * len(loaded)
+    groups = {}
+    for index, (sampling_frequency, data) in enumerate(loaded):
+        if data.dtype == np.int16:
+            pcm = data if data.ndim == 2 else data[:, np.newaxis]
+            groups.setdefault((int(sampling_frequency), pcm.shape), []).append((index, pcm))
+        else:  # the reference's own route
+            audio_signal = data / pow(2, data.itemsize * 8 - 1) if data.dtype.kind in "iu" else data.astype(float)
+            if audio_signal.ndim == 1:
+                audio_signal = audio_signal[:, np.newaxis]
+            result = _host.separate_f64(method, audio_signal, sampling_frequency, _tunables(), spectrograms=False)
+            wavwrite(result["background"], sampling_frequency, output_files[index])
+            integers[index] = result["integers"]
+    for (sampling_frequency, _), members in groups.items():
+        batch = np.stack([pcm for _, pcm in members])
+        background, ints = _host.separate_batch(method, batch, sampling_frequency, _tunables(), in_format="pcm16",
+                                                out_format="pcm16", devices=devices)
+        for slot, (index, _) in enumerate(members):
+            scipy.io.wavfile.write(output_files[index], sampling_frequency, background[slot])
+            integers[index] = ints[slot]
+    return integers
+
+
 def pinned_empty(shape, dtype=np.float32):
     """An uninitialised NumPy array on page-locked host memory; keep the returned holder alive while the array is
     in use: `holder = repet.pinned_empty(shape); x = holder.array`."""

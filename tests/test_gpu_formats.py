@@ -160,3 +160,55 @@ def test_one_long_track_split_by_time_block(repet):
         assert err <= tol, "%s: %.3e" % (name, err)
     params, _ = repet._host.derive_params(FS, repet._tunables(), "extended")
     assert len(repet._host.track_time_blocks("extended", len(x), params, 3)) == 3
+
+
+def test_wave_files_in_wave_files_out(repet, tmp_path, wav_pcm):
+    """repet.separate_files: int16 WAVE files through the PCM16 batch path (the bundled clip of BASELINE config 1 and
+    two synthetic ones of another length), written back as int16; checked against wavread -> original."""
+    import scipy.io.wavfile
+
+    clips = {"bundled": wav_pcm[: 9 * FS]}
+    for i in range(2):
+        audio = repet_synth.make_clip(980 + i, 7 * FS)
+        clips["synth%d" % i] = np.clip(np.rint(audio.T * 32768.0), -32768, 32767).astype(np.int16)
+    inputs, outputs = [], []
+    for name, pcm in clips.items():
+        inputs.append(str(tmp_path / (name + ".wav")))
+        outputs.append(str(tmp_path / (name + "_background.wav")))
+        scipy.io.wavfile.write(inputs[-1], FS, pcm)
+    periods = repet.separate_files(inputs, outputs, "original")
+    for path_in, path_out, period in zip(inputs, outputs, periods):
+        audio_signal, fs = repet.wavread(path_in)
+        y_ref, det = oracle.original(audio_signal, fs, return_details=True)
+        assert int(period[0]) == det["period"]
+        fs_out, written = scipy.io.wavfile.read(path_out)
+        assert fs_out == FS and written.dtype == np.int16 and written.shape == y_ref.shape
+        err = np.max(np.abs(written / 32768.0 - y_ref))
+        assert err <= 2.0 ** -16 + 1e-4 * np.max(np.abs(y_ref)), err
+
+
+def test_bench_line_contract(repet):
+    """bench.py on a small batch: the JSON line carries every key of the contract (roofline, cpu_baseline, e2e with
+    its copy bytes, host_link, gpu_launches, clocks, configs)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--clips-per-gpu", "16", "--steps", "2", "--warmup", "3",
+                          "--configs", "cfg1", "--cpu-sample-clips", "2"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "cpu_baseline", "e2e",
+                "e2e_pcm16", "e2e_numpy_f64", "host_link", "configs"):
+        assert key in line, key
+    assert line["unit"] == "audio-s/s" and line["scaling"] == "weak" and line["dtype"] == "f32" and line["value"] > 0
+    assert line["gpu_launches"] == 7 * line["steps"]
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["bound"] == "hbm"
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["periods_equal_gpu"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 16 * 2 * 30 * FS * 4 and line["e2e"]["value"] > 0
+    assert line["e2e_pcm16"]["h2d_bytes_per_step"] * 2 == line["e2e"]["h2d_bytes_per_step"]
+    assert line["configs"]["cfg1"]["period"] == 286
+    assert "workload" in line["config"] and "model" not in line["config"]
