@@ -645,17 +645,57 @@ __device__ void gen_localmaxima(const double* __restrict__ v, int n, double thr,
     if (threadIdx.x == 0) *cnt_out = min(K, number);
     __syncthreads();
 }
-// REPET-SIM: the similar-frame list of every column of S (repet.py:1370-1381); one CTA per column, row in smem
+// REPET-SIM: the similar-frame list of every column of S (repet.py:1370-1381).  Persistent CTAs walk the columns; a
+// column (= row of the symmetric S) is examined in chunks of GEN_IDX_CHUNK elements staged in shared memory with a
+// halo of d on both sides, so a track of any length fits; the survivors' indices go to a per-CTA global scratch list
+// and are ranked by value (ties: descending index) as _localmaxima does.
+constexpr int GEN_IDX_CHUNK = 4096;
 __global__ void __launch_bounds__(512)
-k_gen_indices(const double* __restrict__ S, int T, double thr, int d, int number, int* __restrict__ idx, int* __restrict__ cnt) {
+k_gen_indices(const double* __restrict__ S, int T, double thr, int d, int number, int* __restrict__ idx, int* __restrict__ cnt,
+              int* __restrict__ kept_scratch) {
     extern __shared__ __align__(16) unsigned char gsm[];
-    double* v = reinterpret_cast<double*>(gsm);
-    int* kept = reinterpret_cast<int*>(v + T);
+    double* v = reinterpret_cast<double*>(gsm);  // [GEN_IDX_CHUNK + 2 d]
     __shared__ int s_count;
-    const int c = blockIdx.x;
-    for (int i = threadIdx.x; i < T; i += blockDim.x) v[i] = S[(long long)c * T + i];
-    __syncthreads();
-    gen_localmaxima(v, T, thr, d, number, kept, &s_count, idx + (long long)c * number, cnt + c, 0, 0);
+    int* __restrict__ kept = kept_scratch + (size_t)blockIdx.x * T;
+    for (int c = blockIdx.x; c < T; c += gridDim.x) {
+        const double* __restrict__ row = S + (long long)c * T;
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = 0;
+        for (int g0 = 0; g0 < T; g0 += GEN_IDX_CHUNK) {
+            __syncthreads();
+            const int n_stage = min(GEN_IDX_CHUNK, T - g0) + 2 * d;
+            for (int x = threadIdx.x; x < n_stage; x += blockDim.x) {
+                const int g = g0 - d + x;
+                v[x] = (g >= 0 && g < T) ? row[g] : -INFINITY;  // beyond the ends: clipped windows (never above a value)
+            }
+            __syncthreads();
+            for (int x = threadIdx.x; x < min(GEN_IDX_CHUNK, T - g0); x += blockDim.x) {
+                const double a = v[x + d];
+                bool keep = a >= thr;
+                for (int u = x; u <= x + 2 * d && keep; ++u)
+                    if (u != x + d && !(a > v[u])) {
+                        // -inf padding stands for "no neighbour": it must not veto a maximum of value -inf itself
+                        const int g = g0 - d + u;
+                        if (g >= 0 && g < T) keep = false;
+                    }
+                if (keep) kept[atomicAdd(&s_count, 1)] = g0 + x;
+            }
+        }
+        __syncthreads();
+        const int K = s_count;
+        for (int q = threadIdx.x; q < K; q += blockDim.x) {
+            const int i = kept[q];
+            const double a = row[i];
+            int rank = 0;
+            for (int r = 0; r < K; ++r) {
+                const int io = kept[r];
+                const double b = row[io];
+                rank += (b > a) || (b == a && io > i);
+            }
+            if (rank < number) idx[(long long)c * number + rank] = i;
+        }
+        if (threadIdx.x == 0) cnt[c] = min(K, number);
+    }
 }
 // online REPET-SIM: frame j >= B-1 against the B frames of its ring buffer in SLOT order (repet.py:834-866, quirk Q6)
 // Rows are frames base .. base + T - 1 of a longer stream (base = repet_params.online_frame_base; 0 for a whole
@@ -955,10 +995,15 @@ int gen_run(repet_handle* h, int method, const double* d_audio, long long S, int
             if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory for the similarity matrix");
             dim3 grid((unsigned)((T + 63) / 64), (unsigned)((T + 63) / 64));
             k_gen_gram<<<grid, 256, 0, st>>>(An, T, F, Sm);
-            const size_t smem = (size_t)T * 12 + 16;
-            if (smem > 220 * 1024) return fail(h, REPET_E_UNSUPPORTED, "track too long for the general similar-frame selection");
+            const size_t smem = (size_t)(GEN_IDX_CHUNK + 2 * (size_t)p->similarity_distance) * sizeof(double);
+            if (smem > 200 * 1024) return fail(h, REPET_E_UNSUPPORTED, "similarity_distance too long for the general similar-frame selection");
             if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gen_indices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_gen_indices<<<(unsigned)T, 512, smem, st>>>(Sm, (int)T, p->similarity_threshold, p->similarity_distance, number, idx, cnt);
+            const int n_ctas = (int)std::min<long long>(T, 2LL * h->sm_count);
+            int* kept_scratch = pool.get<int>((size_t)n_ctas * T);
+            if (!pool.ok) return fail(h, REPET_E_OOM, "out of device memory in the general path");
+            k_gen_indices<<<n_ctas, 512, smem, st>>>(Sm, (int)T, p->similarity_threshold, p->similarity_distance, number, idx, cnt,
+                                                     kept_scratch);
+            pool.release(kept_scratch);
             pool.release(Sm);
         }
         mode = 2;

@@ -214,3 +214,16 @@ def test_stream_at_general_shapes_matches_the_whole_signal_call(repet):
         assert streamed.shape == whole.shape
         _signal_close(streamed, whole, "stream %d Hz %d ch" % (fs, channels), tol=1e-12)
         _signal_close(whole, oracle.simonline(x, fs), "whole vs oracle %d Hz %d ch" % (fs, channels))
+
+
+def test_general_sim_on_a_track_longer_than_one_selection_chunk(repet):
+    """The general path's similar-frame selection walks a column in chunks of 4096 frames with halos; a 100 s
+    three-channel track (T = 4308) crosses a chunk boundary.  Lists and signal against the oracle."""
+    x = repet_synth.make_clip(990, 100 * FS, 3, redraw_seconds=(20, 30)).T.astype(np.float64)
+    y, lists = repet._host.sim_f64(x, FS, repet._tunables(), return_indices=True)
+    with np.errstate(all="ignore"):
+        y_ref, det = oracle.sim(x, FS, return_details=True)
+    assert len(lists) == len(det["indices"]) == 4308
+    bad = [i for i, (a, b) in enumerate(zip(lists, det["indices"])) if not np.array_equal(a, b)]
+    assert not bad, "lists differ at frames %s" % bad[:8]
+    _signal_close(y, y_ref, "general sim, 100 s, 3 channels")
