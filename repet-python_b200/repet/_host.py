@@ -406,12 +406,16 @@ def original_batch(audio, sampling_frequency, tunables, handle=None, out=None):
     handle.ensure_window(params.window_length)
     background = out if out is not None else np.empty_like(audio)
     periods = np.zeros(number_clips, dtype=np.int32)
-    handle.check(
-        handle.lib.repet_original_batch(
-            handle.h, _ptr(audio), number_clips, number_channels, number_samples, ctypes.byref(params),
-            _ptr(background), _ptr(periods),
+    try:
+        handle.check(
+            handle.lib.repet_original_batch(
+                handle.h, _ptr(audio), number_clips, number_channels, number_samples, ctypes.byref(params),
+                _ptr(background), _ptr(periods),
+            )
         )
-    )
+    except NotImplementedError:  # e.g. a period range above 1024 frames: the general path has no such limit
+        background, ints = _separate_batch_general("original", audio, 0, 0, sampling_frequency, tunables, handle, out)
+        return background, ints[:, 0]
     return background, periods
 
 
@@ -759,12 +763,15 @@ def driver_batch(driver, audio, sampling_frequency, tunables, handle=None):
         raise ValueError("unknown driver %r" % driver)
     background = np.empty_like(audio)
     ints = np.zeros((number_clips, max(1, per_clip)), dtype=np.int32)
-    handle.check(
-        getattr(handle.lib, "repet_%s_batch" % driver)(
-            handle.h, _ptr(audio), number_clips, number_channels, number_samples, ctypes.byref(params), _ptr(background),
-            _ptr(ints),
+    try:
+        handle.check(
+            getattr(handle.lib, "repet_%s_batch" % driver)(
+                handle.h, _ptr(audio), number_clips, number_channels, number_samples, ctypes.byref(params), _ptr(background),
+                _ptr(ints),
+            )
         )
-    )
+    except NotImplementedError:
+        return _separate_batch_general(driver, audio, 0, 0, sampling_frequency, tunables, handle, None)
     return background, ints
 
 
@@ -860,7 +867,10 @@ def separate_batch(driver, audio, sampling_frequency, tunables, handle=None, in_
             ctypes.byref(params), _ptr(out[first:stop]), out_code, _ptr(ints[first:stop])))
 
     if devices is None:
-        run(handle or get_handle(), 0, number_clips)
+        try:
+            run(handle or get_handle(), 0, number_clips)
+        except NotImplementedError:  # a shape or tunable the fast kernels refuse (e.g. a period range above 1024 frames)
+            return _separate_batch_general(driver, audio, in_code, out_code, sampling_frequency, tunables, handle, out)
         return out, ints
     devices = [int(d) for d in devices]
     if not devices:

@@ -227,3 +227,21 @@ def test_general_sim_on_a_track_longer_than_one_selection_chunk(repet):
     bad = [i for i, (a, b) in enumerate(zip(lists, det["indices"])) if not np.array_equal(a, b)]
     assert not bad, "lists differ at frames %s" % bad[:8]
     _signal_close(y, y_ref, "general sim, 100 s, 3 channels")
+
+
+def test_batches_fall_back_to_the_general_path_when_the_fast_kernels_refuse(repet):
+    """A period range above 1024 frames inside a BATCH call: the fast path answers REPET_E_UNSUPPORTED, the batch
+    wrappers route the clips through the general path (the single-clip wrappers already did)."""
+    audio = repet_synth.make_batch(995, 2, 90 * FS)
+    saved = repet.period_range
+    try:
+        repet.period_range = [1, 29]  # 1249 frames
+        background, periods = repet.original_batch(audio, FS)
+        sep, ints = repet.separate_batch(audio, FS, "original")
+    finally:
+        repet.period_range = saved
+    assert np.array_equal(ints[:, 0], periods) and np.array_equal(sep, background)
+    for i in range(2):
+        y_ref, det = oracle.original(audio[i].T.astype(np.float64), FS, return_details=True, period_range=(1, 29))
+        assert int(periods[i]) == det["period"]
+        _signal_close(background[i].T.astype(np.float64), y_ref, "clip %d" % i, tol=1e-6)
